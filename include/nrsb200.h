@@ -1,0 +1,173 @@
+/*
+ * nrsb200.h -- C ABI of the B200-native pressure-Poisson path (drop-in for nekRS v23.0's
+ * elliptic / oogs / linAlg device path).  Plain C: pointers and sizes only.
+ *
+ * Conventions
+ *   - Every function returns NRSB_OK (0) or a negative NRSB_ERR_* code; never exits/aborts
+ *     (the reference aborts through nrsAbort/MPI_Abort, nrssys.hpp:86-108; the adapter maps codes).
+ *     nrsb_last_error_string() describes the last failure on the calling thread.
+ *   - Pointers named d_* / documented "device" are CUDA device pointers (what occa::memory::ptr()
+ *     returns); "host" pointers are ordinary memory.  `stream` is a cudaStream_t passed as void*.
+ *   - Types as in nrssys.hpp: dfloat=double, pfloat=float, dlong=int32, hlong=int64.
+ *   - `precision` is sizeof(element): 8 (dfloat) or 4 (pfloat) -- the reference selects the same
+ *     two instances by kernel-name suffix ("..._<N>pfloat", registerEllipticKernels.cpp:166-195).
+ *   - One handle <-> one host thread <-> one device.  No hidden device-wide synchronisation except
+ *     where a scalar is returned to the host.
+ *
+ * Each entry point cites the reference interface it replaces (file:line under /root/reference).
+ */
+#ifndef NRSB200_H
+#define NRSB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NRSB_OK 0
+#define NRSB_ERR_INVALID (-1) /* bad argument / unsupported configuration */
+#define NRSB_ERR_CUDA (-2)    /* CUDA runtime error (message has the cudaError string) */
+#define NRSB_ERR_NOMEM (-3)
+#define NRSB_ERR_DIVERGED (-4) /* NaN residual (PCG.cpp:193-195) */
+
+typedef int32_t nrsb_dlong;
+typedef int64_t nrsb_hlong;
+
+const char* nrsb_last_error_string(void);
+const char* nrsb_version(void);
+
+/* ---- device plumbing (platform->device.malloc / occa::memory::copyFrom/copyTo) ------------- */
+int nrsb_device_count(int* count);
+int nrsb_set_device(int device);
+int nrsb_malloc(void** d_ptr, size_t bytes);
+int nrsb_free(void* d_ptr);
+int nrsb_malloc_host(void** h_ptr, size_t bytes); /* pinned */
+int nrsb_free_host(void* h_ptr);
+int nrsb_memcpy_h2d(void* d_dst, const void* h_src, size_t bytes, void* stream);
+int nrsb_memcpy_d2h(void* h_dst, const void* d_src, size_t bytes, void* stream);
+int nrsb_memcpy_d2d(void* d_dst, const void* d_src, size_t bytes, void* stream);
+int nrsb_memset(void* d_dst, int value, size_t bytes, void* stream);
+int nrsb_stream_synchronize(void* stream);
+int nrsb_device_synchronize(void);
+int nrsb_l2_flush(void* stream); /* writes a >L2-sized scratch buffer (benchmark hygiene) */
+/* CUDA events for device-side timing on the launching stream (timer::tic/toc, timer.cpp:199-233) */
+int nrsb_event_create(void** event);
+int nrsb_event_destroy(void* event);
+int nrsb_event_record(void* event, void* stream);
+int nrsb_event_synchronize(void* event);
+int nrsb_event_elapsed_ms(void* start, void* stop, float* ms);
+int nrsb_stream_create(void** stream);
+int nrsb_stream_destroy(void* stream);
+
+/* ---- kernel-level entry points (one per reference kernel, reference argument order) -------- */
+
+/* ellipticPartialAxCoeffHex3D  (kernels/elliptic/ellipticPartialAxCoeffHex3D.okl:1..1444, serial
+ * twin .c:2-12; called from ellipticAx, ellipticOperator.cpp:83-93).
+ * Nq = N+1 in 2..12.  D_host: HOST pointer to the Nq*Nq row-major derivative matrix
+ * D[i][m] = l_m'(r_i) (mesh->D); the reference's extra `S = D^T` argument is derived from it.
+ * poisson != 0 : p_poisson build (lambda1 ignored); lambda_field != 0 : p_lambda=1 (per-node
+ * coefficients, `ELLIPTIC COEFF FIELD`), else lambda0[0]/lambda1[0] are scalars on the device.
+ * variant: 0 slab kernel, 1 pencil kernel, -1 library default for (Nq, precision). */
+int nrsb_ellipticPartialAxCoeffHex3D(int Nq, int precision, int variant, nrsb_dlong Nelements, nrsb_dlong offset,
+                                     nrsb_dlong loffset, const nrsb_dlong* d_elementList, const void* d_ggeo,
+                                     const void* D_host, const void* d_lambda0, const void* d_lambda1, int poisson,
+                                     int lambda_field, const void* d_q, void* d_Aq, void* stream);
+
+/* mask  (kernels/core/mask.okl; ellipticApplyMask.cpp:3-27) */
+int nrsb_mask(int precision, nrsb_dlong Nmasked, const nrsb_dlong* d_maskIds, void* d_q, void* stream);
+
+/* gatherScatterMany_{float,double}Add  (3rd_party/gslib/ogs/okl/gatherScatterMany.okl) */
+int nrsb_gatherScatterMany_add(int precision, nrsb_dlong Ngather, int Nentries, nrsb_dlong stride,
+                               const nrsb_dlong* d_gatherStarts, const nrsb_dlong* d_gatherIds, void* d_q,
+                               void* stream);
+
+/* linAlg (src/linAlg/linAlg.hpp:33-282; kernels/linAlg/*.okl).  Scalars by value. */
+int nrsb_fill(int precision, nrsb_dlong N, double alpha, void* d_a, void* stream);
+int nrsb_axpby(int precision, nrsb_dlong N, double alpha, const void* d_x, double beta, void* d_y, void* stream);
+int nrsb_axpbyMany(int precision, nrsb_dlong N, int Nfields, nrsb_dlong offset, double alpha, const void* d_x,
+                   double beta, void* d_y, void* stream);
+int nrsb_axmyz(int precision, nrsb_dlong N, double alpha, const void* d_x, const void* d_y, void* d_z, void* stream);
+int nrsb_scale(int precision, nrsb_dlong N, double alpha, void* d_x, void* stream);
+int nrsb_copyDfloatToPfloat(nrsb_dlong N, const double* d_x, float* d_y, void* stream);
+int nrsb_copyPfloatToDfloat(nrsb_dlong N, const float* d_x, double* d_y, void* stream);
+/* reductions return the (rank-local) value to the host: they synchronise the stream. */
+int nrsb_weightedInnerProdMany(nrsb_dlong N, int Nfields, nrsb_dlong offset, const double* d_w, const double* d_x,
+                               const double* d_y, double* result, void* stream);
+int nrsb_weightedNorm2Many(nrsb_dlong N, int Nfields, nrsb_dlong offset, const double* d_w, const double* d_x,
+                           double* result, void* stream);
+int nrsb_weightedInnerProdMulti(nrsb_dlong N, int NVec, nrsb_dlong offset, const double* d_w, const double* d_x,
+                                const double* d_y, double* results, void* stream);
+int nrsb_sum(int precision, nrsb_dlong N, const void* d_x, double* result, void* stream);
+/* ellipticBlockUpdatePCG (kernels/elliptic/ellipticBlockUpdatePCG.okl:26-111, PCG.cpp:33-83):
+ * r -= alpha Ap, returns sum w r^2; if d_x and d_p are non-NULL also x += alpha p (fused). */
+int nrsb_ellipticBlockUpdatePCG(nrsb_dlong N, nrsb_dlong offset, const double* d_invDegree, const double* d_Ap,
+                                double alpha, double* d_r, const double* d_p, double* d_x, double* rdotr,
+                                void* stream);
+int nrsb_updateChebyshev(nrsb_dlong N, float dCoeff, float rCoeff, const float* d_SAd, float* d_d, float* d_r,
+                         float* d_x, void* stream);
+int nrsb_updateFourthKindChebyshev(nrsb_dlong N, float beta, const float* d_Ad, const float* d_d, float* d_r,
+                                   float* d_x, void* stream);
+int nrsb_gramSchmidtOrthogonalization(nrsb_dlong N, nrsb_dlong offset, int gmresSize, const double* d_weights,
+                                      const double* d_y, const double* d_V, double* d_w, double* result,
+                                      void* stream);
+int nrsb_updatePGMRESSolution(nrsb_dlong N, nrsb_dlong offset, int gmresSize, const double* d_y, const double* d_Z,
+                              double* d_x, void* stream);
+int nrsb_fusedResidualAndNorm(nrsb_dlong N, nrsb_dlong offset, const double* d_weights, const double* d_b,
+                              const double* d_Ax, double* d_r, double* result, void* stream);
+
+/* Schwarz / FDM  (kernels/elliptic/{preFDM,fusedFDM,postFDM}.okl; ellipticMultiGridSchwarz.cpp:1056-1156).
+ * Nq is the ELEMENT Nq; the extended size is Nq+2.  pfloat only (production precision). */
+int nrsb_preFDM(int Nq, nrsb_dlong Nelements, const float* d_u, float* d_work1, void* stream);
+int nrsb_fusedFDM(int Nq, int restrict_, nrsb_dlong Nelements, const nrsb_dlong* d_elementList, float* d_Su,
+                  const float* d_Sx, const float* d_Sy, const float* d_Sz, const float* d_invL, const float* d_wts,
+                  float* d_u, void* stream);
+int nrsb_postFDM(int Nq, nrsb_dlong Nelements, float* d_work1, float* d_work2, float* d_Su, const float* d_wts,
+                 void* stream);
+
+/* p-multigrid transfers (kernels/elliptic/ellipticPrecon{Coarsen,Prolongate}Hex3D.okl).
+ * R_host: HOST pointer, R[NqC][NqF] pfloat (ellipticMultiGridLevelSetup.cpp:238-258). */
+int nrsb_ellipticPreconCoarsenHex3D(int NqF, int NqC, nrsb_dlong Nelements, const float* R_host, const float* d_qf,
+                                    float* d_qc, void* stream);
+int nrsb_ellipticPreconProlongateHex3D(int NqF, int NqC, nrsb_dlong Nelements, const float* R_host,
+                                       const float* d_qc, float* d_qN, void* stream);
+
+/* geometricFactorsHex3D (kernels/mesh/geometricFactorsHex3D.okl:26-142): ggeo[E][7][Np], host D/gllw */
+int nrsb_geometricFactorsHex3D(int Nq, nrsb_dlong Nelements, const double* D_host, const double* gllw_host,
+                               const double* d_x, const double* d_y, const double* d_z, double* d_ggeo,
+                               double* d_jacobian, void* stream);
+
+/* ---- gather-scatter handles  (ogs_t / oogs_t, 3rd_party/gslib/ogs/ogs.hpp:145-295) ------------ */
+typedef struct nrsb_ogs* nrsb_ogs_t;
+
+/* topology of ids shared with other ranks, discovered by the bootstrap layer (the reference gets it
+ * from gslib gs_setup over MPI, ogsSetup.cpp:150-175).  NULL / nranks==1 for a single rank. */
+typedef struct {
+  int rank, nranks;
+  int64_t nShared;
+  const nrsb_hlong* sharedIds; /* ascending global ids present on this rank AND another one */
+  const int32_t* sharerOffsets; /* nShared+1 */
+  const int32_t* sharerRanks;   /* ascending ranks sharing each id, this rank included */
+} nrsb_shared_topology;
+
+/* ogsSetup (ogsSetup.cpp:111-397).  ids: HOST, 0 = ignored node. */
+int nrsb_ogs_setup(nrsb_dlong N, const nrsb_hlong* ids_host, const nrsb_shared_topology* topo, nrsb_ogs_t* out);
+int nrsb_ogs_destroy(nrsb_ogs_t ogs);
+/* sizes: {N, Nlocal, NlocalGather, Nhalo, NhaloGather, nPairs, nQuads, nOcts, nGen} */
+int nrsb_ogs_sizes(nrsb_ogs_t ogs, int64_t sizes[9]);
+/* copies of the reference-layout maps for parity tests (HOST buffers, caller sized via nrsb_ogs_sizes) */
+int nrsb_ogs_get_local_maps(nrsb_ogs_t ogs, nrsb_dlong* gatherOffsets, nrsb_dlong* gatherIds);
+int nrsb_ogs_get_halo_maps(nrsb_ogs_t ogs, nrsb_dlong* gatherOffsets, nrsb_dlong* gatherIds, nrsb_hlong* baseIds);
+int nrsb_ogs_get_inv_degree(nrsb_ogs_t ogs, double* invDegree_host);
+int nrsb_ogs_inv_degree_device(nrsb_ogs_t ogs, const double** d_invDegree, const float** d_invDegreePfloat);
+/* oogs::startFinish (oogs.cpp:823-837) with ogsAdd on one rank: in-place v <- Q Q^T v, k fields.
+ * d_maskIds may be NULL; when given the ids are zeroed in the same launch (they must not belong to
+ * any gather row, i.e. the handle was built from masked ids as in ellipticOgs.cpp:126-131). */
+int nrsb_ogs_gather_scatter(nrsb_ogs_t ogs, int precision, int k, nrsb_dlong stride, nrsb_dlong Nmasked,
+                            const nrsb_dlong* d_maskIds, void* d_v, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NRSB200_H */

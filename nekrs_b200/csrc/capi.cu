@@ -1,0 +1,523 @@
+// capi.cu -- extern "C" surface declared in include/nrsb200.h (kernel-level + plumbing + ogs).
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "gs.hpp"
+#include "kernels.hpp"
+#include "linalg.hpp"
+
+namespace nrsb {
+
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& s) { g_last_error = s; }
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line)
+{
+  char buf[512];
+  snprintf(buf, sizeof(buf), "CUDA error %d (%s) in %s at %s:%d", (int)e, cudaGetErrorString(e), what, file, line);
+  g_last_error = buf;
+  return NRSB_ERR_CUDA;
+}
+
+int ax_default_variant(int Nq, int precision)
+{
+  (void)precision;
+  return Nq >= 3 ? 1 : 0;
+}
+
+// process-wide scratch for the kernel-level reductions that return a value to the host
+struct HostReduce {
+  ReduceWs ws;
+  double* d_out = nullptr;
+  double* h_out = nullptr;  // pinned
+  int device = -1;
+  int ensure()
+  {
+    int dev;
+    NRSB_CUDA(cudaGetDevice(&dev));
+    if (dev == device && ws.partials) return NRSB_OK;
+    device = dev;
+    NRSB_CUDA(cudaMalloc((void**)&ws.partials, sizeof(double) * kMaxRedBlocks * kMaxRed));
+    NRSB_CUDA(cudaMalloc((void**)&ws.ticket, sizeof(unsigned)));
+    NRSB_CUDA(cudaMemset(ws.ticket, 0, sizeof(unsigned)));
+    NRSB_CUDA(cudaMalloc((void**)&d_out, sizeof(double) * kMaxRed));
+    NRSB_CUDA(cudaMallocHost((void**)&h_out, sizeof(double) * kMaxRed));
+    return NRSB_OK;
+  }
+  int fetch(int nv, double* result, cudaStream_t s)
+  {
+    NRSB_CUDA(cudaMemcpyAsync(h_out, d_out, sizeof(double) * nv, cudaMemcpyDeviceToHost, s));
+    NRSB_CUDA(cudaStreamSynchronize(s));
+    for (int v = 0; v < nv; ++v) result[v] = h_out[v];
+    return NRSB_OK;
+  }
+};
+static HostReduce g_red;
+static std::mutex g_red_mutex;
+
+static void* g_flush_buf = nullptr;
+static size_t g_flush_bytes = 0;
+
+}  // namespace nrsb
+
+using namespace nrsb;
+
+#define ST(s) ((cudaStream_t)(s))
+#define PREC_OK(p) NRSB_REQUIRE((p) == 8 || (p) == 4, "precision must be 8 (dfloat) or 4 (pfloat)")
+
+extern "C" {
+
+const char* nrsb_last_error_string(void) { return g_last_error.c_str(); }
+const char* nrsb_version(void) { return "nrsb200 0.1 (sm_100a)"; }
+
+int nrsb_device_count(int* count)
+{
+  NRSB_CUDA(cudaGetDeviceCount(count));
+  return NRSB_OK;
+}
+int nrsb_set_device(int device)
+{
+  NRSB_CUDA(cudaSetDevice(device));
+  return NRSB_OK;
+}
+int nrsb_malloc(void** d_ptr, size_t bytes)
+{
+  *d_ptr = nullptr;
+  if (bytes == 0) return NRSB_OK;
+  cudaError_t e = cudaMalloc(d_ptr, bytes);
+  if (e == cudaErrorMemoryAllocation) {
+    cudaGetLastError();
+    set_last_error("cudaMalloc: out of device memory");
+    return NRSB_ERR_NOMEM;
+  }
+  NRSB_CUDA(e);
+  return NRSB_OK;
+}
+int nrsb_free(void* d_ptr)
+{
+  NRSB_CUDA(cudaFree(d_ptr));
+  return NRSB_OK;
+}
+int nrsb_malloc_host(void** h_ptr, size_t bytes)
+{
+  NRSB_CUDA(cudaMallocHost(h_ptr, bytes));
+  return NRSB_OK;
+}
+int nrsb_free_host(void* h_ptr)
+{
+  NRSB_CUDA(cudaFreeHost(h_ptr));
+  return NRSB_OK;
+}
+int nrsb_memcpy_h2d(void* d, const void* h, size_t bytes, void* stream)
+{
+  NRSB_CUDA(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ST(stream)));
+  return NRSB_OK;
+}
+int nrsb_memcpy_d2h(void* h, const void* d, size_t bytes, void* stream)
+{
+  NRSB_CUDA(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, ST(stream)));
+  return NRSB_OK;
+}
+int nrsb_memcpy_d2d(void* dst, const void* src, size_t bytes, void* stream)
+{
+  NRSB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ST(stream)));
+  return NRSB_OK;
+}
+int nrsb_memset(void* d, int value, size_t bytes, void* stream)
+{
+  NRSB_CUDA(cudaMemsetAsync(d, value, bytes, ST(stream)));
+  return NRSB_OK;
+}
+int nrsb_stream_synchronize(void* stream)
+{
+  NRSB_CUDA(cudaStreamSynchronize(ST(stream)));
+  return NRSB_OK;
+}
+int nrsb_device_synchronize(void)
+{
+  NRSB_CUDA(cudaDeviceSynchronize());
+  return NRSB_OK;
+}
+int nrsb_l2_flush(void* stream)
+{
+  const size_t bytes = 256u << 20;  // 2 x L2
+  if (!g_flush_buf) {
+    NRSB_CUDA(cudaMalloc(&g_flush_buf, bytes));
+    g_flush_bytes = bytes;
+  }
+  NRSB_CUDA(cudaMemsetAsync(g_flush_buf, 1, g_flush_bytes, ST(stream)));
+  return NRSB_OK;
+}
+
+int nrsb_event_create(void** event)
+{
+  cudaEvent_t e;
+  NRSB_CUDA(cudaEventCreate(&e));
+  *event = (void*)e;
+  return NRSB_OK;
+}
+int nrsb_event_destroy(void* event)
+{
+  NRSB_CUDA(cudaEventDestroy((cudaEvent_t)event));
+  return NRSB_OK;
+}
+int nrsb_event_record(void* event, void* stream)
+{
+  NRSB_CUDA(cudaEventRecord((cudaEvent_t)event, ST(stream)));
+  return NRSB_OK;
+}
+int nrsb_event_synchronize(void* event)
+{
+  NRSB_CUDA(cudaEventSynchronize((cudaEvent_t)event));
+  return NRSB_OK;
+}
+int nrsb_event_elapsed_ms(void* start, void* stop, float* ms)
+{
+  NRSB_CUDA(cudaEventElapsedTime(ms, (cudaEvent_t)start, (cudaEvent_t)stop));
+  return NRSB_OK;
+}
+int nrsb_stream_create(void** stream)
+{
+  cudaStream_t s;
+  NRSB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  *stream = (void*)s;
+  return NRSB_OK;
+}
+int nrsb_stream_destroy(void* stream)
+{
+  NRSB_CUDA(cudaStreamDestroy(ST(stream)));
+  return NRSB_OK;
+}
+
+// ------------------------------------------------------------------------------------------ kernels
+int nrsb_ellipticPartialAxCoeffHex3D(int Nq, int precision, int variant, nrsb_dlong Nelements, nrsb_dlong offset,
+                                     nrsb_dlong loffset, const nrsb_dlong* d_elementList, const void* d_ggeo,
+                                     const void* D_host, const void* d_lambda0, const void* d_lambda1, int poisson,
+                                     int lambda_field, const void* d_q, void* d_Aq, void* stream)
+{
+  (void)offset;
+  PREC_OK(precision);
+  NRSB_REQUIRE(Nelements >= 0, "Nelements < 0");
+  NRSB_REQUIRE(D_host != nullptr, "D_host is NULL");
+  if (variant < 0) variant = ax_default_variant(Nq, precision);
+  if (precision == 8)
+    return ax_launch<double>(Nq, variant, Nelements, loffset, d_elementList, (const double*)d_ggeo,
+                             (const double*)D_host, (const double*)d_lambda0, (const double*)d_lambda1, poisson,
+                             lambda_field, (const double*)d_q, (double*)d_Aq, ST(stream));
+  return ax_launch<float>(Nq, variant, Nelements, loffset, d_elementList, (const float*)d_ggeo, (const float*)D_host,
+                          (const float*)d_lambda0, (const float*)d_lambda1, poisson, lambda_field, (const float*)d_q,
+                          (float*)d_Aq, ST(stream));
+}
+
+int nrsb_mask(int precision, nrsb_dlong Nmasked, const nrsb_dlong* d_maskIds, void* d_q, void* stream)
+{
+  PREC_OK(precision);
+  return precision == 8 ? mask_launch<double>(Nmasked, d_maskIds, (double*)d_q, ST(stream))
+                        : mask_launch<float>(Nmasked, d_maskIds, (float*)d_q, ST(stream));
+}
+
+int nrsb_gatherScatterMany_add(int precision, nrsb_dlong Ngather, int Nentries, nrsb_dlong stride,
+                               const nrsb_dlong* d_gatherStarts, const nrsb_dlong* d_gatherIds, void* d_q,
+                               void* stream)
+{
+  PREC_OK(precision);
+  return precision == 8
+             ? gs_csr_launch<double>(Ngather, Nentries, stride, d_gatherStarts, d_gatherIds, (double*)d_q, ST(stream))
+             : gs_csr_launch<float>(Ngather, Nentries, stride, d_gatherStarts, d_gatherIds, (float*)d_q, ST(stream));
+}
+
+int nrsb_fill(int precision, nrsb_dlong N, double alpha, void* d_a, void* stream)
+{
+  PREC_OK(precision);
+  return precision == 8 ? fill_launch<double>(N, alpha, (double*)d_a, ST(stream))
+                        : fill_launch<float>(N, (float)alpha, (float*)d_a, ST(stream));
+}
+int nrsb_axpby(int precision, nrsb_dlong N, double alpha, const void* d_x, double beta, void* d_y, void* stream)
+{
+  PREC_OK(precision);
+  return precision == 8 ? axpby_launch<double>(N, DevScalar::host(alpha), (const double*)d_x, DevScalar::host(beta),
+                                               (double*)d_y, ST(stream))
+                        : axpby_launch<float>(N, DevScalar::host(alpha), (const float*)d_x, DevScalar::host(beta),
+                                              (float*)d_y, ST(stream));
+}
+int nrsb_axpbyMany(int precision, nrsb_dlong N, int Nfields, nrsb_dlong offset, double alpha, const void* d_x,
+                   double beta, void* d_y, void* stream)
+{
+  PREC_OK(precision);
+  for (int f = 0; f < Nfields; ++f) {
+    const size_t o = (size_t)f * offset * precision;
+    int rc = nrsb_axpby(precision, N, alpha, (const char*)d_x + o, beta, (char*)d_y + o, stream);
+    if (rc) return rc;
+  }
+  return NRSB_OK;
+}
+int nrsb_axmyz(int precision, nrsb_dlong N, double alpha, const void* d_x, const void* d_y, void* d_z, void* stream)
+{
+  PREC_OK(precision);
+  return precision == 8
+             ? axmyz_launch<double>(N, alpha, (const double*)d_x, (const double*)d_y, (double*)d_z, ST(stream))
+             : axmyz_launch<float>(N, (float)alpha, (const float*)d_x, (const float*)d_y, (float*)d_z, ST(stream));
+}
+int nrsb_scale(int precision, nrsb_dlong N, double alpha, void* d_x, void* stream)
+{
+  PREC_OK(precision);
+  return precision == 8 ? scale_launch<double>(N, alpha, (double*)d_x, ST(stream))
+                        : scale_launch<float>(N, (float)alpha, (float*)d_x, ST(stream));
+}
+int nrsb_copyDfloatToPfloat(nrsb_dlong N, const double* d_x, float* d_y, void* stream)
+{
+  return copy_d2f_launch(N, d_x, d_y, ST(stream));
+}
+int nrsb_copyPfloatToDfloat(nrsb_dlong N, const float* d_x, double* d_y, void* stream)
+{
+  return copy_f2d_launch(N, d_x, d_y, ST(stream));
+}
+
+#define WITH_RED(body)                                  \
+  std::lock_guard<std::mutex> lk(g_red_mutex);          \
+  {                                                     \
+    int rc0 = g_red.ensure();                           \
+    if (rc0) return rc0;                                \
+  }                                                     \
+  body
+
+int nrsb_weightedInnerProdMany(nrsb_dlong N, int Nfields, nrsb_dlong offset, const double* d_w, const double* d_x,
+                               const double* d_y, double* result, void* stream)
+{
+  WITH_RED({
+    double tot = 0;
+    for (int f = 0; f < Nfields; ++f) {
+      int rc = wdot_launch<double>(N, d_w, d_x + (size_t)f * offset, d_y + (size_t)f * offset, g_red.d_out, g_red.ws,
+                                   ST(stream));
+      if (rc) return rc;
+      double v;
+      if ((rc = g_red.fetch(1, &v, ST(stream)))) return rc;
+      tot += v;
+    }
+    *result = tot;
+    return NRSB_OK;
+  })
+}
+int nrsb_weightedNorm2Many(nrsb_dlong N, int Nfields, nrsb_dlong offset, const double* d_w, const double* d_x,
+                           double* result, void* stream)
+{
+  WITH_RED({
+    double tot = 0;
+    for (int f = 0; f < Nfields; ++f) {
+      int rc = wnorm2_launch<double>(N, d_w, d_x + (size_t)f * offset, g_red.d_out, g_red.ws, ST(stream));
+      if (rc) return rc;
+      double v;
+      if ((rc = g_red.fetch(1, &v, ST(stream)))) return rc;
+      tot += v;
+    }
+    *result = tot;
+    return NRSB_OK;
+  })
+}
+int nrsb_weightedInnerProdMulti(nrsb_dlong N, int NVec, nrsb_dlong offset, const double* d_w, const double* d_x,
+                                const double* d_y, double* results, void* stream)
+{
+  WITH_RED({
+    int rc = wdot_multi_launch(N, NVec, offset, d_w, d_x, d_y, g_red.d_out, g_red.ws, ST(stream));
+    if (rc) return rc;
+    return g_red.fetch(NVec, results, ST(stream));
+  })
+}
+int nrsb_sum(int precision, nrsb_dlong N, const void* d_x, double* result, void* stream)
+{
+  PREC_OK(precision);
+  WITH_RED({
+    int rc = precision == 8 ? sum_launch<double>(N, (const double*)d_x, g_red.d_out, g_red.ws, ST(stream))
+                            : sum_launch<float>(N, (const float*)d_x, g_red.d_out, g_red.ws, ST(stream));
+    if (rc) return rc;
+    return g_red.fetch(1, result, ST(stream));
+  })
+}
+int nrsb_ellipticBlockUpdatePCG(nrsb_dlong N, nrsb_dlong offset, const double* d_invDegree, const double* d_Ap,
+                                double alpha, double* d_r, const double* d_p, double* d_x, double* rdotr,
+                                void* stream)
+{
+  (void)offset;
+  WITH_RED({
+    int rc = update_pcg_launch(N, d_invDegree, d_Ap, d_p, DevScalar::host(alpha), d_r, (d_p && d_x) ? d_x : nullptr,
+                               g_red.d_out, g_red.ws, ST(stream));
+    if (rc) return rc;
+    return g_red.fetch(1, rdotr, ST(stream));
+  })
+}
+int nrsb_updateChebyshev(nrsb_dlong N, float dCoeff, float rCoeff, const float* d_SAd, float* d_d, float* d_r,
+                         float* d_x, void* stream)
+{
+  return update_chebyshev_launch(N, dCoeff, rCoeff, d_SAd, d_d, d_r, d_x, ST(stream));
+}
+int nrsb_updateFourthKindChebyshev(nrsb_dlong N, float beta, const float* d_Ad, const float* d_d, float* d_r,
+                                   float* d_x, void* stream)
+{
+  return update_fourth_chebyshev_launch(N, beta, d_Ad, d_d, d_r, d_x, ST(stream));
+}
+int nrsb_gramSchmidtOrthogonalization(nrsb_dlong N, nrsb_dlong offset, int gmresSize, const double* d_weights,
+                                      const double* d_y, const double* d_V, double* d_w, double* result,
+                                      void* stream)
+{
+  WITH_RED({
+    int rc = gram_schmidt_launch(N, offset, gmresSize, d_weights, d_y, d_V, d_w, g_red.d_out, g_red.ws, ST(stream));
+    if (rc) return rc;
+    return g_red.fetch(1, result, ST(stream));
+  })
+}
+int nrsb_updatePGMRESSolution(nrsb_dlong N, nrsb_dlong offset, int gmresSize, const double* d_y, const double* d_Z,
+                              double* d_x, void* stream)
+{
+  return update_pgmres_solution_launch(N, offset, gmresSize, d_y, d_Z, d_x, ST(stream));
+}
+int nrsb_fusedResidualAndNorm(nrsb_dlong N, nrsb_dlong offset, const double* d_weights, const double* d_b,
+                              const double* d_Ax, double* d_r, double* result, void* stream)
+{
+  (void)offset;
+  WITH_RED({
+    int rc = fused_residual_and_norm_launch(N, d_weights, d_b, d_Ax, d_r, g_red.d_out, g_red.ws, ST(stream));
+    if (rc) return rc;
+    return g_red.fetch(1, result, ST(stream));
+  })
+}
+
+int nrsb_preFDM(int Nq, nrsb_dlong Nelements, const float* d_u, float* d_work1, void* stream)
+{
+  return pre_fdm_launch(Nq, Nelements, d_u, d_work1, ST(stream));
+}
+int nrsb_fusedFDM(int Nq, int restrict_, nrsb_dlong Nelements, const nrsb_dlong* d_elementList, float* d_Su,
+                  const float* d_Sx, const float* d_Sy, const float* d_Sz, const float* d_invL, const float* d_wts,
+                  float* d_u, void* stream)
+{
+  NRSB_REQUIRE(!restrict_ || d_wts, "RAS (restrict=1) needs wts");
+  return fused_fdm_launch(Nq, restrict_, Nelements, d_elementList, d_Su, d_Sx, d_Sy, d_Sz, d_invL, d_wts, d_u,
+                          ST(stream));
+}
+int nrsb_postFDM(int Nq, nrsb_dlong Nelements, float* d_work1, float* d_work2, float* d_Su, const float* d_wts,
+                 void* stream)
+{
+  return post_fdm_launch(Nq, Nelements, d_work1, d_work2, d_Su, d_wts, ST(stream));
+}
+int nrsb_ellipticPreconCoarsenHex3D(int NqF, int NqC, nrsb_dlong Nelements, const float* R_host, const float* d_qf,
+                                    float* d_qc, void* stream)
+{
+  return transfer_dispatch(true, NqF, NqC, Nelements, R_host, d_qf, d_qc, ST(stream));
+}
+int nrsb_ellipticPreconProlongateHex3D(int NqF, int NqC, nrsb_dlong Nelements, const float* R_host,
+                                       const float* d_qc, float* d_qN, void* stream)
+{
+  return transfer_dispatch(false, NqF, NqC, Nelements, R_host, d_qc, d_qN, ST(stream));
+}
+int nrsb_geometricFactorsHex3D(int Nq, nrsb_dlong Nelements, const double* D_host, const double* gllw_host,
+                               const double* d_x, const double* d_y, const double* d_z, double* d_ggeo,
+                               double* d_jacobian, void* stream)
+{
+  NRSB_REQUIRE(Nq >= 2 && Nq <= kMaxNq, "Nq out of range");
+  double* d_tmp = nullptr;
+  NRSB_CUDA(cudaMalloc((void**)&d_tmp, sizeof(double) * (Nq * Nq + Nq)));
+  NRSB_CUDA(cudaMemcpyAsync(d_tmp, D_host, sizeof(double) * Nq * Nq, cudaMemcpyHostToDevice, ST(stream)));
+  NRSB_CUDA(cudaMemcpyAsync(d_tmp + Nq * Nq, gllw_host, sizeof(double) * Nq, cudaMemcpyHostToDevice, ST(stream)));
+  int rc = geometric_factors_launch(Nq, Nelements, d_tmp, d_tmp + Nq * Nq, d_x, d_y, d_z, d_ggeo, d_jacobian,
+                                    ST(stream));
+  cudaStreamSynchronize(ST(stream));
+  cudaFree(d_tmp);
+  return rc;
+}
+
+// ------------------------------------------------------------------------------------------ ogs
+struct nrsb_ogs {
+  ogs_t impl;
+};
+
+int nrsb_ogs_setup(nrsb_dlong N, const nrsb_hlong* ids_host, const nrsb_shared_topology* topo, nrsb_ogs_t* out)
+{
+  NRSB_REQUIRE(out != nullptr, "out is NULL");
+  NRSB_REQUIRE(N >= 0, "N < 0");
+  NRSB_REQUIRE(N == 0 || ids_host != nullptr, "ids is NULL");
+  SharedTopology t;
+  const SharedTopology* tp = nullptr;
+  if (topo && topo->nranks > 1) {
+    t.rank = topo->rank;
+    t.nranks = topo->nranks;
+    t.nShared = topo->nShared;
+    t.sharedIds = (const hlong*)topo->sharedIds;
+    t.sharerOffsets = topo->sharerOffsets;
+    t.sharerRanks = topo->sharerRanks;
+    tp = &t;
+  }
+  nrsb_ogs* h = new nrsb_ogs();
+  int rc = h->impl.setup(N, (const hlong*)ids_host, tp);
+  if (rc) {
+    delete h;
+    return rc;
+  }
+  *out = h;
+  return NRSB_OK;
+}
+int nrsb_ogs_destroy(nrsb_ogs_t ogs)
+{
+  delete ogs;
+  return NRSB_OK;
+}
+int nrsb_ogs_sizes(nrsb_ogs_t ogs, int64_t s[9])
+{
+  NRSB_REQUIRE(ogs, "ogs is NULL");
+  const ogs_t& o = ogs->impl;
+  s[0] = o.N;
+  s[1] = o.Nlocal;
+  s[2] = o.NlocalGather;
+  s[3] = o.Nhalo;
+  s[4] = o.NhaloGather;
+  s[5] = o.rows.nPairs;
+  s[6] = o.rows.nQuads;
+  s[7] = o.rows.nOcts;
+  s[8] = o.rows.nGen;
+  return NRSB_OK;
+}
+int nrsb_ogs_get_local_maps(nrsb_ogs_t ogs, nrsb_dlong* gatherOffsets, nrsb_dlong* gatherIds)
+{
+  NRSB_REQUIRE(ogs, "ogs is NULL");
+  const ogs_t& o = ogs->impl;
+  std::memcpy(gatherOffsets, o.localGatherOffsets.data(), o.localGatherOffsets.size() * sizeof(dlong));
+  if (!o.localGatherIds.empty())
+    std::memcpy(gatherIds, o.localGatherIds.data(), o.localGatherIds.size() * sizeof(dlong));
+  return NRSB_OK;
+}
+int nrsb_ogs_get_halo_maps(nrsb_ogs_t ogs, nrsb_dlong* gatherOffsets, nrsb_dlong* gatherIds, nrsb_hlong* baseIds)
+{
+  NRSB_REQUIRE(ogs, "ogs is NULL");
+  const ogs_t& o = ogs->impl;
+  std::memcpy(gatherOffsets, o.haloGatherOffsets.data(), o.haloGatherOffsets.size() * sizeof(dlong));
+  if (!o.haloGatherIds.empty()) {
+    std::memcpy(gatherIds, o.haloGatherIds.data(), o.haloGatherIds.size() * sizeof(dlong));
+    std::memcpy(baseIds, o.haloBaseIds.data(), o.haloBaseIds.size() * sizeof(hlong));
+  }
+  return NRSB_OK;
+}
+int nrsb_ogs_get_inv_degree(nrsb_ogs_t ogs, double* invDegree_host)
+{
+  NRSB_REQUIRE(ogs, "ogs is NULL");
+  std::memcpy(invDegree_host, ogs->impl.invDegree.data(), ogs->impl.invDegree.size() * sizeof(double));
+  return NRSB_OK;
+}
+int nrsb_ogs_inv_degree_device(nrsb_ogs_t ogs, const double** d_invDegree, const float** d_invDegreePfloat)
+{
+  NRSB_REQUIRE(ogs, "ogs is NULL");
+  if (d_invDegree) *d_invDegree = ogs->impl.d_invDegree;
+  if (d_invDegreePfloat) *d_invDegreePfloat = ogs->impl.d_invDegreePfloat;
+  return NRSB_OK;
+}
+int nrsb_ogs_gather_scatter(nrsb_ogs_t ogs, int precision, int k, nrsb_dlong stride, nrsb_dlong Nmasked,
+                            const nrsb_dlong* d_maskIds, void* d_v, void* stream)
+{
+  NRSB_REQUIRE(ogs, "ogs is NULL");
+  PREC_OK(precision);
+  NRSB_REQUIRE(ogs->impl.NhaloGather == 0, "handle has halo rows: use the oogs exchange API");
+  GsRowsDev R = ogs->impl.rows;
+  R.nMasked = d_maskIds ? Nmasked : 0;
+  R.maskIds = d_maskIds;
+  return precision == 8 ? gs_rows_launch<double>(R, k, stride, (double*)d_v, ST(stream))
+                        : gs_rows_launch<float>(R, k, stride, (float*)d_v, ST(stream));
+}
+
+}  // extern "C"

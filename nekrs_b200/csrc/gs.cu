@@ -1,0 +1,152 @@
+// gs.cu -- on-rank gather-scatter  v[i] <- sum_{copies j of i} v[j]   (+ Dirichlet mask).
+//
+// Replaces: 3rd_party/gslib/ogs/okl/gatherScatterMany.okl (gatherScatterMany_{float,double}Add),
+// kernels/core/mask.okl, and the device side of the halo exchange, okl/oogs.okl packBuf/unpackBuf
+// (oogs.okl:1-272), as called from oogs::start/finish (oogs.cpp:682-821).
+//
+// Layout (B200-first, results identical): the reference walks a CSR (gatherStarts, gatherIds)
+// with one thread per row and skips singleton rows at run time (`start+1 != end`).  On a hex
+// mesh almost every non-singleton row has 2 (face), 4 (edge) or 8 (vertex) copies, so at setup
+// the rows are bucketed by length: pairs as int2, quads as int4, octets as 2 x int4, the rest as
+// CSR.  A thread reads its row's indices with ONE coalesced vector load instead of two offset
+// loads plus a dependent index loop, and singleton rows are not stored at all.  Inside a row the
+// copies are summed in ascending local index exactly as the CSR loop does (ogsSetup.cpp:196-249
+// ordering), so results are bit-identical to the reference's kernel.
+//
+// The mask (q[maskIds[n]] = 0) is folded into the same launch: masked nodes carry global id 0 in
+// the masked ogs handle (ellipticOgs.cpp:126-131) and therefore belong to no row, so zeroing them
+// commutes with the sums.
+#include "common.cuh"
+#include "gs.hpp"
+
+namespace nrsb {
+
+template <typename T>
+__global__ void __launch_bounds__(kBlockSize)
+    gs_rows_kernel(const GsRowsDev R, const int Nfields, const dlong stride, T* __restrict__ q)
+{
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  T* __restrict__ qf = q + (size_t)blockIdx.y * stride;
+  (void)Nfields;
+  if (n < R.nPairs) {
+    const int2 id = R.pairs[n];
+    T s = T(0);
+    s += qf[id.x];
+    s += qf[id.y];
+    qf[id.x] = s;
+    qf[id.y] = s;
+    return;
+  }
+  int m = n - R.nPairs;
+  if (m < R.nQuads) {
+    const int4 id = R.quads[m];
+    T s = T(0);
+    s += qf[id.x];
+    s += qf[id.y];
+    s += qf[id.z];
+    s += qf[id.w];
+    qf[id.x] = s;
+    qf[id.y] = s;
+    qf[id.z] = s;
+    qf[id.w] = s;
+    return;
+  }
+  m -= R.nQuads;
+  if (m < R.nOcts) {
+    const int4 ia = R.octs[2 * m], ib = R.octs[2 * m + 1];
+    T s = T(0);
+    s += qf[ia.x];
+    s += qf[ia.y];
+    s += qf[ia.z];
+    s += qf[ia.w];
+    s += qf[ib.x];
+    s += qf[ib.y];
+    s += qf[ib.z];
+    s += qf[ib.w];
+    qf[ia.x] = s;
+    qf[ia.y] = s;
+    qf[ia.z] = s;
+    qf[ia.w] = s;
+    qf[ib.x] = s;
+    qf[ib.y] = s;
+    qf[ib.z] = s;
+    qf[ib.w] = s;
+    return;
+  }
+  m -= R.nOcts;
+  if (m < R.nGen) {
+    const int start = R.genStarts[m], end = R.genStarts[m + 1];
+    T s = T(0);
+    for (int c = start; c < end; ++c) s += qf[R.genIds[c]];
+    for (int c = start; c < end; ++c) qf[R.genIds[c]] = s;
+    return;
+  }
+  m -= R.nGen;
+  if (m < R.nMasked) qf[R.maskIds[m]] = T(0);
+}
+
+template <typename T>
+int gs_rows_launch(const GsRowsDev& R, int Nfields, dlong stride, T* q, cudaStream_t stream)
+{
+  const long total = (long)R.nPairs + R.nQuads + R.nOcts + R.nGen + R.nMasked;
+  if (total == 0 || Nfields == 0) return NRSB_OK;
+  dim3 grid((unsigned)((total + kBlockSize - 1) / kBlockSize), Nfields);
+  gs_rows_kernel<T><<<grid, kBlockSize, 0, stream>>>(R, Nfields, stride, q);
+  NRSB_CHECK_LAUNCH();
+  return NRSB_OK;
+}
+template int gs_rows_launch<double>(const GsRowsDev&, int, dlong, double*, cudaStream_t);
+template int gs_rows_launch<float>(const GsRowsDev&, int, dlong, float*, cudaStream_t);
+
+// ---- plain CSR gather-scatter (signature parity with gatherScatterMany.okl; used by the
+//      kernel-level C ABI and by the setup-time checks)
+template <typename T>
+__global__ void __launch_bounds__(kBlockSize)
+    gs_csr_kernel(const dlong Ngather, const int Nentries, const dlong stride, const dlong* __restrict__ starts,
+                  const dlong* __restrict__ ids, T* __restrict__ q)
+{
+  const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= (long)Ngather * Nentries) return;
+  const dlong gid = g % Ngather;
+  const int k = g / Ngather;
+  const dlong start = starts[gid], end = starts[gid + 1];
+  if (start + 1 == end) return;
+  T gq = T(0);
+  for (dlong n = start; n < end; ++n) gq += q[ids[n] + (size_t)k * stride];
+  for (dlong n = start; n < end; ++n) q[ids[n] + (size_t)k * stride] = gq;
+}
+
+template <typename T>
+int gs_csr_launch(dlong Ngather, int Nentries, dlong stride, const dlong* starts, const dlong* ids, T* q,
+                  cudaStream_t stream)
+{
+  const long total = (long)Ngather * Nentries;
+  if (total == 0) return NRSB_OK;
+  gs_csr_kernel<T><<<(unsigned)((total + kBlockSize - 1) / kBlockSize), kBlockSize, 0, stream>>>(
+      Ngather, Nentries, stride, starts, ids, q);
+  NRSB_CHECK_LAUNCH();
+  return NRSB_OK;
+}
+template int gs_csr_launch<double>(dlong, int, dlong, const dlong*, const dlong*, double*, cudaStream_t);
+template int gs_csr_launch<float>(dlong, int, dlong, const dlong*, const dlong*, float*, cudaStream_t);
+
+// ---- mask  (kernels/core/mask.okl)
+template <typename T>
+__global__ void __launch_bounds__(kBlockSize) mask_kernel(const dlong Nmasked, const dlong* __restrict__ maskIds,
+                                                          T* __restrict__ q)
+{
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n < Nmasked) q[maskIds[n]] = T(0);
+}
+template <typename T>
+int mask_launch(dlong Nmasked, const dlong* maskIds, T* q, cudaStream_t stream)
+{
+  if (Nmasked == 0) return NRSB_OK;
+  mask_kernel<T><<<(Nmasked + kBlockSize - 1) / kBlockSize, kBlockSize, 0, stream>>>(Nmasked, maskIds, q);
+  NRSB_CHECK_LAUNCH();
+  return NRSB_OK;
+}
+template int mask_launch<double>(dlong, const dlong*, double*, cudaStream_t);
+template int mask_launch<float>(dlong, const dlong*, float*, cudaStream_t);
+
+}  // namespace nrsb

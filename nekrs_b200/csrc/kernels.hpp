@@ -1,0 +1,28 @@
+// kernels.hpp -- internal launcher prototypes (one per reference kernel family).
+#pragma once
+#include "common.cuh"
+
+namespace nrsb {
+
+// axhelm.cu
+template <typename T>
+int ax_launch(int Nq, int variant, dlong Nelements, dlong loffset, const dlong* elementList, const T* ggeo,
+              const T* D_host, const T* lambda0, const T* lambda1, int poisson, int lambdaField, const T* q, T* Aq,
+              cudaStream_t stream);
+int ax_default_variant(int Nq, int precision);
+
+// fdm.cu
+int fused_fdm_launch(int Nq, int restrict_, dlong Nelements, const dlong* elementList, float* Su, const float* Sx,
+                     const float* Sy, const float* Sz, const float* invL, const float* wts, float* u,
+                     cudaStream_t stream);
+int pre_fdm_launch(int Nq, dlong Nelements, const float* u, float* work1, cudaStream_t stream);
+int post_fdm_launch(int Nq, dlong Nelements, const float* work1, const float* work2, float* Su, const float* wts,
+                    cudaStream_t stream);
+
+// transfer.cu
+int transfer_dispatch(bool coarsen, int NqF, int NqC, dlong Nelements, const float* R_host, const float* in,
+                      float* out, cudaStream_t stream);
+int geometric_factors_launch(int Nq, dlong Nelements, const double* d_D, const double* d_gllw, const double* x,
+                             const double* y, const double* z, double* ggeo, double* Jac, cudaStream_t stream);
+
+}  // namespace nrsb

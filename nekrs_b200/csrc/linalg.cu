@@ -1,0 +1,350 @@
+// linalg.cu -- streaming BLAS-1 kernels and single-pass weighted reductions.
+//
+// Replaces: kernels/linAlg/*.okl (fill, axpby(Many), axmyz, axmy, scale(Many), add, sum,
+// weightedInnerProd(Many), weightedNorm2(Many), weightedInnerProdMulti, innerProd) and
+// kernels/elliptic/{ellipticBlockUpdatePCG, updateChebyshev, updateFourthKindChebyshev,
+// gramSchmidtOrthogonalization, updatePGMRESSolution, fusedResidualAndNorm}.okl, plus
+// kernels/core/copy{Dfloat,Pfloat}To{Pfloat,Dfloat}.okl.
+//
+// Reductions: the reference writes one partial per 256-thread block, copies all partials to the
+// host, sums them there and calls MPI_Allreduce (linAlg.cpp:986-1034, PCG.cpp:55-74).  Here one
+// launch does everything: grid-stride accumulation in fp64, warp-shuffle + shared-memory block
+// reduction, per-block partials, and the LAST block to finish (atomic ticket) folds the partials
+// in a fixed order, performs the cross-GPU one-shot all-reduce through peer-mapped windows
+// (NVLink stores + flag, comm.cu) and leaves the scalar on the device.  The result is
+// deterministic for a given (N, grid) and bit-identical on every rank.
+#include "linalg.hpp"
+
+namespace nrsb {
+
+constexpr int kRedThreads = 256;
+
+static inline int stream_grid(long N, int perThread = 4)
+{
+  long b = (N + (long)kBlockSize * perThread - 1) / ((long)kBlockSize * perThread);
+  const long cap = (long)kNumSMs * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+// ----------------------------------------------------------------------------- elementwise
+template <typename F>
+__global__ void __launch_bounds__(kBlockSize) ew_kernel(long N, F f)
+{
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) f(i);
+}
+
+template <typename F>
+static int ew_launch(long N, F f, cudaStream_t s)
+{
+  if (N <= 0) return NRSB_OK;
+  ew_kernel<<<stream_grid(N), kBlockSize, 0, s>>>(N, f);
+  NRSB_CHECK_LAUNCH();
+  return NRSB_OK;
+}
+
+template <typename T>
+int fill_launch(long N, T a, T* x, cudaStream_t s)
+{
+  return ew_launch(N, [=] __device__(long i) { x[i] = a; }, s);
+}
+template <typename T>
+int axpby_launch(long N, DevScalar a, const T* x, DevScalar b, T* y, cudaStream_t s)
+{
+  const bool bZero = (b.num == nullptr && b.den == nullptr && b.scale == 0.0);
+  if (bZero)  // y may be uninitialised (linAlg axpby with beta = 0 is used as a scaled copy)
+    return ew_launch(N, [=] __device__(long i) { const T av = (T)a.eval(); y[i] = av * x[i]; }, s);
+  return ew_launch(
+      N,
+      [=] __device__(long i) {
+        const T av = (T)a.eval(), bv = (T)b.eval();
+        y[i] = av * x[i] + bv * y[i];
+      },
+      s);
+}
+template <typename T>
+int axpbyz_launch(long N, DevScalar a, const T* x, DevScalar b, const T* y, T* z, cudaStream_t s)
+{
+  return ew_launch(
+      N,
+      [=] __device__(long i) {
+        const T av = (T)a.eval(), bv = (T)b.eval();
+        z[i] = av * x[i] + bv * y[i];
+      },
+      s);
+}
+template <typename T>
+int axmyz_launch(long N, T a, const T* x, const T* y, T* z, cudaStream_t s)
+{
+  return ew_launch(N, [=] __device__(long i) { z[i] = a * x[i] * y[i]; }, s);
+}
+template <typename T>
+int scale_launch(long N, T a, T* x, cudaStream_t s)
+{
+  return ew_launch(N, [=] __device__(long i) { x[i] *= a; }, s);
+}
+template <typename T>
+int add_scalar_launch(long N, DevScalar a, T* x, cudaStream_t s)
+{
+  return ew_launch(N, [=] __device__(long i) { x[i] += (T)a.eval(); }, s);
+}
+int copy_d2f_launch(long N, const double* x, float* y, cudaStream_t s)
+{
+  return ew_launch(N, [=] __device__(long i) { y[i] = (float)x[i]; }, s);
+}
+int copy_f2d_launch(long N, const float* x, double* y, cudaStream_t s)
+{
+  return ew_launch(N, [=] __device__(long i) { y[i] = (double)x[i]; }, s);
+}
+int axmyz_mixed_launch(long N, float a, const double* x, const float* y, double* z, cudaStream_t s)
+{
+  // axmyzManyPfloat.c: z = dfloat(alpha * x * y)
+  return ew_launch(N, [=] __device__(long i) { z[i] = (double)(a * x[i] * y[i]); }, s);
+}
+int update_chebyshev_launch(long N, float dCoeff, float rCoeff, const float* SAd, float* d, float* r, float* x,
+                            cudaStream_t s)
+{
+  return ew_launch(
+      N,
+      [=] __device__(long i) {
+        const float dn = d[i];
+        const float rn = r[i] - SAd[i];
+        x[i] = x[i] + dn;
+        r[i] = rn;
+        d[i] = dCoeff * dn + rCoeff * rn;
+      },
+      s);
+}
+int update_fourth_chebyshev_launch(long N, float beta, const float* Ad, const float* d, float* r, float* x,
+                                   cudaStream_t s)
+{
+  return ew_launch(
+      N,
+      [=] __device__(long i) {
+        x[i] = x[i] + beta * d[i];
+        r[i] = r[i] - Ad[i];
+      },
+      s);
+}
+int update_pgmres_solution_launch(long N, long offset, int gmresSize, const double* y, const double* Z, double* x,
+                                  cudaStream_t s)
+{
+  return ew_launch(
+      N,
+      [=] __device__(long i) {
+        double xv = x[i];
+        for (int j = 0; j < gmresSize; ++j) xv += Z[i + (size_t)j * offset] * y[j];
+        x[i] = xv;
+      },
+      s);
+}
+
+#define NRSB_INST(T)                                                                                  \
+  template int fill_launch<T>(long, T, T*, cudaStream_t);                                             \
+  template int axpby_launch<T>(long, DevScalar, const T*, DevScalar, T*, cudaStream_t);               \
+  template int axpbyz_launch<T>(long, DevScalar, const T*, DevScalar, const T*, T*, cudaStream_t);    \
+  template int axmyz_launch<T>(long, T, const T*, const T*, T*, cudaStream_t);                        \
+  template int scale_launch<T>(long, T, T*, cudaStream_t);                                            \
+  template int add_scalar_launch<T>(long, DevScalar, T*, cudaStream_t);
+NRSB_INST(double)
+NRSB_INST(float)
+#undef NRSB_INST
+
+// ----------------------------------------------------------------------------- reductions
+__device__ __forceinline__ double block_sum(double v, double* s_red)
+{
+  // s_red: kRedThreads/32 doubles.  Result valid in thread 0.
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) s_red[wid] = v;
+  __syncthreads();
+  if (wid == 0) {
+    v = (lane < kRedThreads / 32) ? s_red[lane] : 0.0;
+    v = warp_sum(v);
+  }
+  return v;
+}
+
+// cross-rank one-shot all-reduce executed by thread 0 of the last block (see comm.cu)
+__device__ void peer_allreduce(const PeerReduce& P, double* vals, int nv);
+
+template <int NV, typename Op>
+__global__ void __launch_bounds__(kRedThreads) reduce_kernel(long N, Op op, int nv, double* out, ReduceWs ws)
+{
+  __shared__ double s_red[kRedThreads / 32];
+  __shared__ bool s_last;
+  double acc[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) acc[v] = 0.0;
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) op(i, acc);
+
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const double b = block_sum(acc[v], s_red);
+    if (threadIdx.x == 0 && v < nv) ws.partials[(size_t)blockIdx.x * kMaxRed + v] = b;
+  }
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned t = atomicAdd(ws.ticket, 1u);
+    s_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  double tot[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    double a = 0.0;
+    if (v < nv)
+      for (int b = threadIdx.x; b < (int)gridDim.x; b += kRedThreads)
+        a += __ldcg(&ws.partials[(size_t)b * kMaxRed + v]);
+    tot[v] = block_sum(a, s_red);
+  }
+  if (threadIdx.x == 0) {
+    if (ws.peer.nranks > 1) peer_allreduce(ws.peer, tot, nv);
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+      if (v < nv) out[v] = tot[v];
+    *ws.ticket = 0u;
+  }
+}
+
+__device__ void peer_allreduce(const PeerReduce& P, double* vals, int nv)
+{
+  // epoch e, parity-double-buffered slots: slots[p] = peer p's window [2][nranks][kMaxRed]
+  const unsigned long long e = *P.epoch + 1ull;
+  *P.epoch = e;
+  const int par = (int)(e & 1ull);
+  for (int p = 0; p < P.nranks; ++p) {
+    double* dst = P.slots[p] + ((size_t)par * P.nranks + P.rank) * kMaxRed;
+    for (int v = 0; v < nv; ++v) dst[v] = vals[v];
+  }
+  __threadfence_system();
+  for (int p = 0; p < P.nranks; ++p) {
+    volatile unsigned long long* f = P.flags[p] + P.rank;
+    *f = e;
+  }
+  volatile unsigned long long* mine = P.flags[P.rank];
+  const volatile double* loc = P.slots[P.rank] + (size_t)par * P.nranks * kMaxRed;
+  for (int v = 0; v < nv; ++v) vals[v] = 0.0;
+  for (int p = 0; p < P.nranks; ++p) {
+    while (mine[p] < e) {
+    }
+    __threadfence_system();
+    for (int v = 0; v < nv; ++v) vals[v] += loc[(size_t)p * kMaxRed + v];
+  }
+}
+
+static inline int red_grid(long N)
+{
+  long b = (N + (long)kRedThreads * 8 - 1) / ((long)kRedThreads * 8);
+  if (b > kMaxRedBlocks) b = kMaxRedBlocks;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+template <int NV, typename Op>
+static int reduce_launch(long N, Op op, int nv, double* out, const ReduceWs& ws, cudaStream_t s)
+{
+  if (!ws.partials || !ws.ticket) {
+    set_last_error("reduction workspace not initialised");
+    return NRSB_ERR_INVALID;
+  }
+  reduce_kernel<NV, Op><<<red_grid(N), kRedThreads, 0, s>>>(N, op, nv, out, ws);
+  NRSB_CHECK_LAUNCH();
+  return NRSB_OK;
+}
+
+template <typename T>
+int wdot_launch(long N, const T* w, const T* x, const T* y, double* out, const ReduceWs& ws, cudaStream_t s)
+{
+  return reduce_launch<1>(
+      N, [=] __device__(long i, double* acc) { acc[0] += (double)x[i] * (double)y[i] * (double)w[i]; }, 1, out, ws,
+      s);
+}
+template <typename T>
+int wnorm2_launch(long N, const T* w, const T* x, double* out, const ReduceWs& ws, cudaStream_t s)
+{
+  return reduce_launch<1>(
+      N,
+      [=] __device__(long i, double* acc) {
+        const double xv = (double)x[i];
+        acc[0] += xv * xv * (double)w[i];
+      },
+      1, out, ws, s);
+}
+template <typename T>
+int sum_launch(long N, const T* x, double* out, const ReduceWs& ws, cudaStream_t s)
+{
+  return reduce_launch<1>(N, [=] __device__(long i, double* acc) { acc[0] += (double)x[i]; }, 1, out, ws, s);
+}
+int dot_launch(long N, const double* x, const double* y, double* out, const ReduceWs& ws, cudaStream_t s)
+{
+  return reduce_launch<1>(N, [=] __device__(long i, double* acc) { acc[0] += x[i] * y[i]; }, 1, out, ws, s);
+}
+template int wdot_launch<double>(long, const double*, const double*, const double*, double*, const ReduceWs&,
+                                 cudaStream_t);
+template int wdot_launch<float>(long, const float*, const float*, const float*, double*, const ReduceWs&,
+                                cudaStream_t);
+template int wnorm2_launch<double>(long, const double*, const double*, double*, const ReduceWs&, cudaStream_t);
+template int wnorm2_launch<float>(long, const float*, const float*, double*, const ReduceWs&, cudaStream_t);
+template int sum_launch<double>(long, const double*, double*, const ReduceWs&, cudaStream_t);
+template int sum_launch<float>(long, const float*, double*, const ReduceWs&, cudaStream_t);
+
+int wdot_multi_launch(long N, int NVec, long offset, const double* w, const double* X, const double* y, double* out,
+                      const ReduceWs& ws, cudaStream_t s)
+{
+  if (NVec < 1 || NVec > kMaxRed) {
+    set_last_error("weightedInnerProdMulti: NVec must be in 1..16");
+    return NRSB_ERR_INVALID;
+  }
+  auto op = [=] __device__(long i, double* acc) {
+    const double wy = w[i] * y[i];
+#pragma unroll
+    for (int v = 0; v < kMaxRed; ++v)
+      if (v < NVec) acc[v] += wy * X[i + (size_t)v * offset];
+  };
+  return reduce_launch<kMaxRed>(N, op, NVec, out, ws, s);
+}
+
+int update_pcg_launch(long N, const double* w, const double* Ap, const double* p, DevScalar alpha, double* r,
+                      double* x, double* out, const ReduceWs& ws, cudaStream_t s)
+{
+  auto op = [=] __device__(long i, double* acc) {
+    const double a = alpha.eval();
+    const double rn = r[i] - a * Ap[i];
+    r[i] = rn;
+    if (x) x[i] = a * p[i] + x[i];
+    acc[0] += rn * rn * w[i];
+  };
+  return reduce_launch<1>(N, op, 1, out, ws, s);
+}
+
+int gram_schmidt_launch(long N, long offset, int gmresSize, const double* w, const double* y, const double* V,
+                        double* wv, double* out, const ReduceWs& ws, cudaStream_t s)
+{
+  auto op = [=] __device__(long i, double* acc) {
+    double v = wv[i];
+    for (int j = 0; j < gmresSize; ++j) v -= y[j] * V[i + (size_t)j * offset];
+    wv[i] = v;
+    acc[0] += v * v * w[i];
+  };
+  return reduce_launch<1>(N, op, 1, out, ws, s);
+}
+
+int fused_residual_and_norm_launch(long N, const double* w, const double* b, const double* Ax, double* r, double* out,
+                                   const ReduceWs& ws, cudaStream_t s)
+{
+  auto op = [=] __device__(long i, double* acc) {
+    const double rn = b[i] - Ax[i];
+    r[i] = rn;
+    acc[0] += rn * rn * w[i];
+  };
+  return reduce_launch<1>(N, op, 1, out, ws, s);
+}
+
+}  // namespace nrsb

@@ -1,0 +1,132 @@
+"""CPU checks of the oracle's setup restatement (numpy) and of the mesh generator: the
+reference's own invariants (SURVEY.md §4 "self-checks inside the library") and analytic answers."""
+import numpy as np
+import pytest
+
+from nekrs_b200 import meshgen
+from oracle import sem
+
+
+@pytest.mark.parametrize("N", [1, 2, 3, 5, 7, 9, 11])
+def test_gll_and_dmatrix(N):
+    x, w = sem.jacobi_gll(N)
+    assert abs(w.sum() - 2.0) < 1e-14 and np.allclose(x, -x[::-1], atol=1e-15)
+    # GLL integrates degree 2N-1 exactly
+    for p in range(0, 2 * N, 2):
+        assert abs(np.dot(w, x ** p) - 2.0 / (p + 1)) < 1e-13
+    D = sem.dmatrix_1d(x)
+    for p in range(N + 1):
+        d = p * x ** (p - 1) if p else np.zeros_like(x)
+        assert np.max(np.abs(D @ x ** p - d)) < 1e-11
+    assert np.allclose(meshgen.gll_nodes(N), x, atol=1e-15)
+
+
+def test_interpolation_matrix():
+    xf, _ = sem.jacobi_gll(7)
+    xc, _ = sem.jacobi_gll(3)
+    P = sem.interpolation_matrix_1d(xc, xf)   # coarse -> fine
+    for p in range(4):
+        assert np.max(np.abs(P @ xc ** p - xf ** p)) < 1e-14
+    assert np.allclose(P.sum(axis=1), 1.0)
+
+
+def test_gs_test_c_analytic(orc):
+    """gslib tests/gs_test.c:73-103: a 1-D chain of np 'ranks' each holding ids {r, r+1}: after
+    gs(add) of ones the answers are 2,3,...,3,2 when every rank also holds id 1... restated on one
+    rank: node j of segment r has id r+j+1; interior ids have 2 copies, the ends 1."""
+    nseg = 5
+    ids = np.array([[r + 1, r + 2] for r in range(nseg)], dtype=np.int64).ravel()
+    o = sem.Ogs(ids)
+    v = np.ones(ids.size)
+    orc.gs_add(o, v)
+    expect = np.array([1] + [2] * (2 * nseg - 2) + [1], dtype=float)
+    assert np.array_equal(v, expect)
+    assert np.array_equal(o.inv_degree, 1.0 / expect)
+
+
+@pytest.mark.parametrize("N,nel", [(1, (2, 2, 2)), (3, (3, 2, 2)), (7, (2, 2, 3))])
+def test_ogs_invariants(orc, N, nel):
+    m = meshgen.box_mesh(N, nel)
+    o = sem.Ogs(m.global_ids)
+    nx, ny, nz = nel
+    n_unique = (nx * N + 1) * (ny * N + 1) * (nz * N + 1)
+    assert o.Ngather == n_unique
+    assert o.offsets[-1] == m.global_ids.size
+    # rows ordered by first local index, ascending inside a row (ogsSetup.cpp:196-249)
+    first = o.gather_ids[o.offsets[:-1]]
+    assert np.all(np.diff(first) > 0)
+    for g in range(0, o.Ngather, max(1, o.Ngather // 50)):
+        row = o.gather_ids[o.offsets[g]:o.offsets[g + 1]]
+        assert np.all(np.diff(row) > 0)
+        assert np.all(m.global_ids[row] == m.global_ids[row[0]])
+    # gs(1)*invDegree sums to E*Np within 1e-15 (meshParallelGatherScatterSetup.cpp:136-165)
+    v = np.ones(m.global_ids.size)
+    orc.gs_add(o, v)
+    assert abs(np.sum(v * o.inv_degree) - v.size) / v.size < 1e-15
+    # shared copies agree in position
+    for arr in (m.x, m.y, m.z):
+        a = arr.copy()
+        orc.gs_add(o, a)
+        assert np.max(np.abs(a * o.inv_degree - arr)) < 1e-14
+
+
+def test_geometric_factors_numpy_vs_c(orc):
+    N = 5
+    m = meshgen.box_mesh(N, (2, 3, 2), kershaw_eps=0.3)
+    g, w = sem.jacobi_gll(N)
+    D = sem.dmatrix_1d(g)
+    a, Ja = sem.geometric_factors(m.x, m.y, m.z, N)
+    b, Jb = orc.geometric_factors(m.Nelements, N, D, w, m.x, m.y, m.z)
+    assert np.max(np.abs(a - b)) / np.max(np.abs(b)) < 1e-13
+    assert np.all(Jb > 0)
+    # volume of the kershaw box is 1
+    assert abs(b[:, 6].sum() - 1.0) < 1e-12
+
+
+def test_ax_vs_independent_einsum(orc):
+    """oracle Ax (restated serial kernel) against an independent dense formulation."""
+    N, E = 4, 3
+    Nq, Np = N + 1, (N + 1) ** 3
+    r = np.random.Generator(np.random.PCG64(11))
+    g, _ = sem.jacobi_gll(N)
+    D = sem.dmatrix_1d(g)
+    ggeo = r.random((E, 7, Np))
+    q = r.random(E * Np)
+    out = np.zeros(E * Np)
+    orc.ax(N, np.arange(E, dtype=np.int32), ggeo, D, q, out)
+    Q = q.reshape(E, Nq, Nq, Nq)
+    G = ggeo.reshape(E, 7, Nq, Nq, Nq)
+    qr = np.einsum("im,ekjm->ekji", D, Q)
+    qs = np.einsum("jm,ekmi->ekji", D, Q)
+    qt = np.einsum("km,emji->ekji", D, Q)
+    Gr = G[:, 0] * qr + G[:, 1] * qs + G[:, 4] * qt
+    Gs = G[:, 1] * qr + G[:, 2] * qs + G[:, 3] * qt
+    Gt = G[:, 4] * qr + G[:, 3] * qs + G[:, 5] * qt
+    A = (np.einsum("mi,ekjm->ekji", D, Gr) + np.einsum("mj,ekmi->ekji", D, Gs) + np.einsum("mk,emji->ekji", D, Gt))
+    assert np.max(np.abs(A.ravel() - out)) / np.max(np.abs(out)) < 1e-14
+
+
+def test_kershaw_mesh_properties():
+    m = meshgen.box_mesh(3, (6, 6, 6), kershaw_eps=0.3)
+    assert m.x.min() == -0.5 and m.x.max() == 0.5 and abs(m.y.min() + 0.5) < 1e-15 and abs(m.z.max() - 0.5) < 1e-15
+    _, J = sem.geometric_factors(m.x, m.y, m.z, 3)
+    assert np.all(J > 0)
+    # eps = 1 is the identity map
+    a = meshgen.box_mesh(3, (6, 6, 6), kershaw_eps=1.0)
+    b = meshgen.box_mesh(3, (6, 6, 6))
+    assert np.allclose(a.y, b.y, atol=1e-15) and np.allclose(a.z, b.z, atol=1e-15)
+    # all-Dirichlet boundary flags: 6*36 boundary faces
+    assert (m.EToB == meshgen.DIRICHLET).sum() == 6 * 36
+
+
+def test_partition_covers_mesh():
+    N, nel = 2, (4, 4, 2)
+    whole = meshgen.box_mesh(N, nel)
+    ids = []
+    ne = 0
+    for r in range(4):
+        p = meshgen.box_mesh(N, nel, rank=r, nranks=4)
+        ne += p.Nelements
+        ids.append(p.global_ids)
+    assert ne == whole.Nelements
+    assert np.array_equal(np.unique(np.concatenate(ids)), np.unique(whole.global_ids))
