@@ -167,6 +167,90 @@ int nrsb_ogs_inv_degree_device(nrsb_ogs_t ogs, const double** d_invDegree, const
 int nrsb_ogs_gather_scatter(nrsb_ogs_t ogs, int precision, int k, nrsb_dlong stride, nrsb_dlong Nmasked,
                             const nrsb_dlong* d_maskIds, void* d_v, void* stream);
 
+/* ---- communicator (platform->comm + MPI on this path) ---------------------------------------- */
+/* One process per GPU.  The bootstrap layer (torch.distributed, MPI, ...) supplies two host
+ * collectives used ONLY at setup time (IPC handle / table exchange); every data-path exchange
+ * afterwards is device-initiated over NVLink (oogs halo stores, one-shot scalar all-reduce).
+ * allgather(buf, bytes_per_rank, user): in place, buf holds nranks blocks, block `rank` is valid. */
+typedef struct nrsb_comm* nrsb_comm_t;
+typedef void (*nrsb_allgather_fn)(void* buf, size_t bytes_per_rank, void* user);
+typedef void (*nrsb_barrier_fn)(void* user);
+int nrsb_comm_create(int rank, int nranks, nrsb_allgather_fn allgather, nrsb_barrier_fn barrier, void* user,
+                     nrsb_comm_t* out);
+int nrsb_comm_destroy(nrsb_comm_t comm);
+/* MPI_Allreduce(SUM) of n <= 16 doubles through the device one-shot path (testing / setup) */
+int nrsb_comm_allreduce_sum(nrsb_comm_t comm, int n, double* values_host);
+
+/* multi-rank oogs (oogs::setup / startFinish, oogs.cpp:336-837): exchange over NVLink peer windows */
+typedef struct nrsb_oogs* nrsb_oogs_t;
+int nrsb_oogs_setup(nrsb_ogs_t ogs, nrsb_comm_t comm, int maxFields, nrsb_oogs_t* out);
+int nrsb_oogs_destroy(nrsb_oogs_t oogs);
+int nrsb_oogs_start(nrsb_oogs_t oogs, int precision, int k, nrsb_dlong stride, void* d_v, void* stream);
+int nrsb_oogs_finish(nrsb_oogs_t oogs, int precision, int k, nrsb_dlong stride, void* d_v, void* stream);
+
+/* ---- elliptic solver handle  (elliptic_t, elliptic.h:73-238) ------------------------------------ */
+typedef struct nrsb_elliptic* nrsb_elliptic_t;
+
+typedef struct {
+  int N;                        /* polynomial order of the solve (mesh->N) */
+  nrsb_dlong Nelements;         /* elements on this rank */
+  const double *x, *y, *z;      /* HOST node coordinates [Nelements*Np] (mesh->x/y/z) */
+  const nrsb_hlong* globalIds;  /* HOST C0 numbering, >= 1 (mesh->globalIds) */
+  const int* EToB;              /* HOST [Nelements*6] boundary flag per face: 0 interior, 1 DIRICHLET, 4 NEUMANN */
+  const nrsb_shared_topology* topo; /* sharing of globalIds across ranks; NULL on one rank */
+  /* coarser p-multigrid meshes: numbering (and sharing) at each level order (createMeshMG) */
+  int nLevels;
+  const int* levelOrders;
+  const nrsb_hlong* const* levelGlobalIds;
+  const nrsb_shared_topology* const* levelTopo; /* NULL on one rank */
+  /* setupAide options of the solver section, "KEY=VALUE" lines, keys as in the reference
+   * (SOLVER, PRECONDITIONER, MULTIGRID SMOOTHER, MAXIMUM ITERATIONS, SOLVER TOLERANCE, ...) */
+  const char* options;
+  int poisson;                  /* elliptic->poisson */
+  double lambda0, lambda1;      /* constant coefficients (o_lambda0/o_lambda1) */
+  nrsb_comm_t comm;             /* NULL on one rank */
+  const char* name;             /* "pressure" */
+} nrsb_elliptic_config;
+
+/* ellipticSolveSetup (ellipticSetup.cpp:116-327) */
+int nrsb_elliptic_setup(const nrsb_elliptic_config* cfg, nrsb_elliptic_t* out);
+int nrsb_elliptic_destroy(nrsb_elliptic_t h);
+/* ellipticSolve (ellipticSolve.cpp:32-190): d_r = rhs (overwritten), d_x = initial guess in / solution out;
+ * both fieldOffset doubles on the device.  Returns Niter and the three norms of elliptic.h:89-90. */
+int nrsb_elliptic_solve(nrsb_elliptic_t h, double* d_r, double* d_x, int* Niter, double* res00Norm, double* res0Norm,
+                        double* resNorm);
+/* same with HOST vectors of Nlocal doubles (copies in and out included) */
+int nrsb_elliptic_solve_host(nrsb_elliptic_t h, const double* rhs_host, double* x_host, int* Niter, double* res00Norm,
+                             double* res0Norm, double* resNorm);
+/* ellipticOperator (ellipticOperator.cpp:117-172): Aq = Q Q^T mask (A q); level = multigrid level index
+ * (0 = the fp64 solver itself when precision = 8; fp32 instances live on the MG levels) */
+int nrsb_elliptic_operator(nrsb_elliptic_t h, int level, int precision, const void* d_q, void* d_Aq, int masked);
+int nrsb_elliptic_operator_host(nrsb_elliptic_t h, const double* q_host, double* Aq_host);
+/* ellipticAx on the full element list */
+int nrsb_elliptic_ax(nrsb_elliptic_t h, int level, int precision, const void* d_q, void* d_Aq);
+/* ellipticPreconditioner (ellipticPreconditioner.cpp:33-84) */
+int nrsb_elliptic_preconditioner(nrsb_elliptic_t h, double* d_r, double* d_z);
+/* pMGLevel::smoothSchwarz / smooth / coarsen / prolongate on level `level` (pfloat vectors) */
+int nrsb_elliptic_level_op(nrsb_elliptic_t h, int level, const char* op, float* d_in, float* d_out);
+/* integer / real properties: "Nlocal","fieldOffset","Nmasked","nLevels","overlap","allNeumann",
+ * "NglobalGatherElements","NlocalGatherElements","coarseIterations"; per level (key "level<k>:<name>"):
+ * "N","Nlocal","Nmasked","lambda1","lambda0","maxEig","downDegree","upDegree" ; "volume" */
+int nrsb_elliptic_get_int(nrsb_elliptic_t h, const char* key, int64_t* value);
+int nrsb_elliptic_get_real(nrsb_elliptic_t h, const char* key, double* value);
+/* arrays (HOST out): "maskIds" (int32), "invDegree" (double), "resHistory" (double, length Niter),
+ * "level<k>:invDegree", "level<k>:maskIds", "level<k>:Sx|Sy|Sz|invL|wts" (float) ; returns count */
+int nrsb_elliptic_get_array(nrsb_elliptic_t h, const char* key, void* out_host, int64_t capacity, int64_t* count);
+int nrsb_elliptic_set_option(nrsb_elliptic_t h, const char* key, const char* value); /* before re-setup of precon */
+int nrsb_elliptic_set_ax_variant(nrsb_elliptic_t h, int precision, int variant);
+int nrsb_elliptic_set_stream(nrsb_elliptic_t h, void* stream);
+/* kernel-variant autotuning as in benchmarkAx (src/bench/axHelm/benchmarkAx.cpp:140-146,289-305) */
+int nrsb_elliptic_autotune(nrsb_elliptic_t h, int* variant_fp64, int* variant_fp32);
+
+/* setup helpers exposed for parity tests */
+int nrsb_gll(int N, double* z_host, double* w_host, double* D_host);
+int nrsb_sym_generalized_eig(int n, double* A_host, double* B_host, double* lam_host);
+int nrsb_spectral_radius(int n, const double* H_host, double* rho);
+
 #ifdef __cplusplus
 }
 #endif

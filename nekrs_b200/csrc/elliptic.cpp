@@ -1,0 +1,681 @@
+// elliptic.cpp -- host control flow of the elliptic solver.
+//
+// Restates, with identical semantics: ellipticSolveSetup (ellipticSetup.cpp:116-327), ellipticOgs
+// (ellipticOgs.cpp:4-134), ellipticAx / ellipticOperator (ellipticOperator.cpp:31-172),
+// ellipticApplyMask (ellipticApplyMask.cpp:3-27), ellipticZeroMean (ellipticZeroMean.cpp:31-44),
+// ellipticSolve (ellipticSolve.cpp:32-190), ellipticPreconditioner (ellipticPreconditioner.cpp:33-84),
+// pcg (PCG.cpp:33-203), pgmres (PGMRES.cpp:31-340), ellipticUpdateJacobi (ellipticUpdateJacobi.cpp:32-115).
+//
+// B200-first differences (results unchanged):
+//  * Krylov scalars stay on the device: dot products are reduced (and all-reduced across GPUs) by
+//    one kernel each and consumed by the next kernel through DevScalar; the host reads ONE value
+//    per iteration (the residual norm, for the convergence test) instead of three blocking
+//    device->host copies + three MPI_Allreduce (PCG.cpp:55-74, linAlg.cpp:1000-1025).
+//  * `r -= alpha Ap`, `x += alpha p` and the weighted norm are a single kernel.
+//  * mask + on-rank gather-scatter + halo unpack are a single kernel after Ax.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "host.hpp"
+#include "projection.hpp"
+
+namespace nrsb {
+
+// device scalar slots
+enum { S_RDOTZ = 0, S_RDOTZ_OLD, S_PAP, S_RDOTR, S_ZDOTAP, S_ALPHA, S_BETA, S_SUM, S_NORM, S_GMRES = 16, S_COUNT = 64 };
+
+elliptic_t::elliptic_t() {}
+elliptic_t::~elliptic_t()
+{
+  if (h_scal) cudaFreeHost(h_scal);
+}
+
+int elliptic_t::read_scalars(int first, int count, double* out)
+{
+  NRSB_CUDA(cudaMemcpyAsync(h_scal + first, o_scal.p + first, sizeof(double) * count, cudaMemcpyDeviceToHost, stream));
+  NRSB_CUDA(cudaStreamSynchronize(stream));
+  for (int i = 0; i < count; ++i) out[i] = h_scal[first + i];
+  return NRSB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// ellipticOgs: Dirichlet mask ids + masked gather-scatter handle
+// ------------------------------------------------------------------------------------------
+static void face_nodes(int N, std::vector<std::vector<int>>& fn)
+{
+  // meshBasisHex3D.cpp:53-82: f0 t=-1, f1 s=-1, f2 r=+1, f3 s=+1, f4 r=-1, f5 t=+1, ascending node index
+  const int Nq = N + 1;
+  fn.assign(6, {});
+  for (int n = 0; n < Nq * Nq * Nq; ++n) {
+    const int i = n % Nq, j = (n / Nq) % Nq, k = n / (Nq * Nq);
+    if (k == 0) fn[0].push_back(n);
+    if (j == 0) fn[1].push_back(n);
+    if (i == N) fn[2].push_back(n);
+    if (j == N) fn[3].push_back(n);
+    if (i == 0) fn[4].push_back(n);
+    if (k == N) fn[5].push_back(n);
+  }
+}
+
+int ellipticOgs(mesh_t* mesh, const std::vector<int>& EToB, elliptic_t* elliptic)
+{
+  const int largeNumber = 1 << 20;
+  const dlong Nlocal = mesh->Nlocal;
+  std::vector<std::vector<int>> fn;
+  face_nodes(mesh->N, fn);
+  // node-wise BC flag, DIRICHLET (lowest id) wins
+  std::vector<double> mapB(Nlocal, (double)largeNumber);
+  for (dlong e = 0; e < mesh->Nelements; ++e)
+    for (int f = 0; f < 6; ++f) {
+      const int bc = EToB[f + (size_t)e * 6];
+      if (bc > 0)
+        for (int n : fn[f]) {
+          double& m = mapB[n + (size_t)e * mesh->Np];
+          m = std::min((double)bc, m);
+        }
+    }
+  // gs-min over the unmasked handle (flags are small integers: exact in fp64)
+  {
+    dbuf<double> d;
+    int rc;
+    if ((rc = d.upload(mapB))) return rc;
+    if ((rc = mesh->oogs->startFinish<double>(d.p, 1, 0, gs_op::min, 0, nullptr, nullptr))) return rc;
+    NRSB_CUDA(cudaDeviceSynchronize());
+    if ((rc = d.download(mapB))) return rc;
+  }
+  elliptic->maskIds.clear();
+  for (dlong n = 0; n < Nlocal; ++n)
+    if (mapB[n] == 1.0) elliptic->maskIds.push_back(n);  // DIRICHLET == 1 (elliptic.h:46)
+  elliptic->Nmasked = (dlong)elliptic->maskIds.size();
+  std::vector<char> isMasked(Nlocal, 0);
+  for (dlong n : elliptic->maskIds) isMasked[n] = 1;
+  std::vector<dlong> loc, glo;
+  for (dlong e : mesh->localGatherElementList)
+    for (int q = 0; q < mesh->Np; ++q)
+      if (isMasked[(size_t)e * mesh->Np + q]) loc.push_back(e * mesh->Np + q);
+  for (dlong e : mesh->globalGatherElementList)
+    for (int q = 0; q < mesh->Np; ++q)
+      if (isMasked[(size_t)e * mesh->Np + q]) glo.push_back(e * mesh->Np + q);
+  elliptic->NmaskedLocal = (dlong)loc.size();
+  elliptic->NmaskedGlobal = (dlong)glo.size();
+  int rc;
+  if ((rc = elliptic->o_maskIds.upload(elliptic->maskIds))) return rc;
+  if ((rc = elliptic->o_maskIdsLocal.upload(loc))) return rc;
+  if ((rc = elliptic->o_maskIdsGlobal.upload(glo))) return rc;
+
+  // masked version of the global numbering (ellipticOgs.cpp:126-131)
+  std::vector<hlong> maskedGlobalIds(mesh->globalIds);
+  for (dlong n : elliptic->maskIds) maskedGlobalIds[n] = 0;
+  elliptic->ogs.reset(new ogs_t());
+  if ((rc = elliptic->ogs->setup(Nlocal, maskedGlobalIds.data(), mesh->topo.nranks > 1 ? &mesh->topo : nullptr)))
+    return rc;
+  elliptic->oogs.reset(new oogs_t());
+  if ((rc = elliptic->oogs->setup(elliptic->ogs.get(), mesh->comm, elliptic->Nfields))) return rc;
+  elliptic->o_invDegree = elliptic->ogs->d_invDegree;
+  elliptic->o_invDegreePfloat = elliptic->ogs->d_invDegreePfloat;
+  return NRSB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+template <typename T>
+struct prec_traits;
+template <>
+struct prec_traits<double> {
+  static const double* ggeo(mesh_t* m) { return m->o_ggeo.p; }
+  static const double* D(mesh_t* m) { return m->D.data(); }
+  static const double* lambda0(elliptic_t* e) { return e->o_lambda0.p; }
+  static const double* lambda1(elliptic_t* e) { return e->o_lambda1.p; }
+  static const double* invDegree(elliptic_t* e) { return e->o_invDegree; }
+  static constexpr int idx = 0;
+};
+template <>
+struct prec_traits<float> {
+  static const float* ggeo(mesh_t* m) { return m->o_ggeoPfloat.p; }
+  static const float* D(mesh_t* m) { return m->Dpfloat.data(); }
+  static const float* lambda0(elliptic_t* e) { return e->o_lambda0Pfloat.p; }
+  static const float* lambda1(elliptic_t* e) { return e->o_lambda1Pfloat.p; }
+  static const float* invDegree(elliptic_t* e) { return e->o_invDegreePfloat; }
+  static constexpr int idx = 1;
+};
+
+template <typename T>
+int ellipticAx(elliptic_t* elliptic, dlong NelementsList, const dlong* o_elementList, const T* o_q, T* o_Aq)
+{
+  if (NelementsList == 0) return NRSB_OK;
+  mesh_t* mesh = elliptic->mesh;
+  using P = prec_traits<T>;
+  NRSB_REQUIRE(P::ggeo(mesh) != nullptr, "geometric factors of the requested precision are not resident");
+  int variant = elliptic->ax_variant[P::idx];
+  if (variant < 0) variant = ax_default_variant(mesh->Nq, (int)sizeof(T));
+  return ax_launch<T>(mesh->Nq, variant, NelementsList, elliptic->loffset, o_elementList, P::ggeo(mesh), P::D(mesh),
+                      P::lambda0(elliptic), P::lambda1(elliptic), elliptic->poisson ? 1 : 0, 0, o_q, o_Aq,
+                      elliptic->stream);
+}
+template int ellipticAx<double>(elliptic_t*, dlong, const dlong*, const double*, double*);
+template int ellipticAx<float>(elliptic_t*, dlong, const dlong*, const float*, float*);
+
+template <typename T>
+int ellipticApplyMask(elliptic_t* elliptic, T* o_x)
+{
+  return mask_launch<T>(elliptic->Nmasked, elliptic->o_maskIds.p, o_x, elliptic->stream);
+}
+template int ellipticApplyMask<double>(elliptic_t*, double*);
+template int ellipticApplyMask<float>(elliptic_t*, float*);
+
+// ellipticOperator (ellipticOperator.cpp:117-172).  With `overlap` the halo elements are done first,
+// their partial sums are pushed to the neighbours (oogs::start), the interior elements follow while
+// the NVLink stores are in flight, and oogs::finish folds everything (and the mask) in one kernel.
+template <typename T>
+int ellipticOperator(elliptic_t* elliptic, const T* o_q, T* o_Aq, bool masked)
+{
+  mesh_t* mesh = elliptic->mesh;
+  oogs_t* oogs = elliptic->oogs.get();
+  int rc;
+  const dlong nm = masked ? elliptic->Nmasked : 0;
+  if (elliptic->overlap) {
+    if ((rc = ellipticAx<T>(elliptic, mesh->NglobalGatherElements, mesh->o_globalGatherElementList.p, o_q, o_Aq)))
+      return rc;
+    if (masked && elliptic->NmaskedGlobal)
+      if ((rc = mask_launch<T>(elliptic->NmaskedGlobal, elliptic->o_maskIdsGlobal.p, o_Aq, elliptic->stream)))
+        return rc;
+    if ((rc = oogs->start<T>(o_Aq, elliptic->Nfields, elliptic->fieldOffset, gs_op::add, elliptic->stream))) return rc;
+    if ((rc = ellipticAx<T>(elliptic, mesh->NlocalGatherElements, mesh->o_localGatherElementList.p, o_q, o_Aq)))
+      return rc;
+    return oogs->finish<T>(o_Aq, elliptic->Nfields, elliptic->fieldOffset, gs_op::add,
+                           masked ? elliptic->NmaskedLocal : 0, elliptic->o_maskIdsLocal.p, elliptic->stream);
+  }
+  if ((rc = ellipticAx<T>(elliptic, mesh->Nelements, mesh->o_elementList.p, o_q, o_Aq))) return rc;
+  if (oogs->ogs->NhaloGather) {
+    // halo rows are packed from masked values: mask first
+    if (nm)
+      if ((rc = mask_launch<T>(nm, elliptic->o_maskIds.p, o_Aq, elliptic->stream))) return rc;
+    return oogs->startFinish<T>(o_Aq, elliptic->Nfields, elliptic->fieldOffset, gs_op::add, 0, nullptr,
+                                elliptic->stream);
+  }
+  return oogs->startFinish<T>(o_Aq, elliptic->Nfields, elliptic->fieldOffset, gs_op::add, nm, elliptic->o_maskIds.p,
+                              elliptic->stream);
+}
+template int ellipticOperator<double>(elliptic_t*, const double*, double*, bool);
+template int ellipticOperator<float>(elliptic_t*, const float*, float*, bool);
+
+int ellipticZeroMean(elliptic_t* elliptic, double* o_q)
+{
+  mesh_t* mesh = elliptic->mesh;
+  const double Nglobal = (double)elliptic->mesh->NelementsGlobal * mesh->Np;
+  int rc;
+  if ((rc = sum_launch<double>(mesh->Nlocal, o_q, elliptic->o_scal.p + S_SUM, elliptic->ws, elliptic->stream)))
+    return rc;
+  DevScalar a = DevScalar::ratio(elliptic->o_scal.p + S_SUM, nullptr, -1.0 / Nglobal);
+  return add_scalar_launch<double>(mesh->Nlocal, a, o_q, elliptic->stream);
+}
+
+// diag(A) (ellipticBlockBuildDiagonalHex3D.okl) is formed by probing-free assembly on the host of the
+// element diagonals from ggeo and D, then gather-scattered and inverted (ellipticUpdateJacobi).
+template <typename T>
+int ellipticBuildDiagonal(elliptic_t* elliptic, T* o_invDiagA)
+{
+  mesh_t* mesh = elliptic->mesh;
+  const int Nq = mesh->Nq, Np = mesh->Np;
+  std::vector<float> gf;
+  std::vector<double> gd;
+  const bool useD = mesh->o_ggeo.p != nullptr;
+  int rc;
+  if (useD) {
+    if ((rc = mesh->o_ggeo.download(gd))) return rc;
+  } else {
+    if ((rc = mesh->o_ggeoPfloat.download(gf))) return rc;
+  }
+  auto G = [&](dlong e, int c, int n) -> double {
+    const size_t id = (size_t)e * 7 * Np + (size_t)c * Np + n;
+    return useD ? gd[id] : (double)gf[id];
+  };
+  const std::vector<double>& D = mesh->D;
+  std::vector<T> diag(mesh->Nlocal);
+  const double lam0 = elliptic->lambda0Value, lam1 = elliptic->poisson ? 0.0 : elliptic->lambda1Value;
+  for (dlong e = 0; e < mesh->Nelements; ++e)
+    for (int k = 0; k < Nq; ++k)
+      for (int j = 0; j < Nq; ++j)
+        for (int i = 0; i < Nq; ++i) {
+          const int n = i + j * Nq + k * Nq * Nq;
+          double r = 0;
+          for (int m = 0; m < Nq; ++m) {
+            r += G(e, 0, m + j * Nq + k * Nq * Nq) * D[m * Nq + i] * D[m * Nq + i];  // G00
+            r += G(e, 2, i + m * Nq + k * Nq * Nq) * D[m * Nq + j] * D[m * Nq + j];  // G11
+            r += G(e, 5, i + j * Nq + m * Nq * Nq) * D[m * Nq + k] * D[m * Nq + k];  // G22
+          }
+          r += 2 * G(e, 1, n) * D[i * Nq + i] * D[j * Nq + j];  // G01
+          r += 2 * G(e, 4, n) * D[i * Nq + i] * D[k * Nq + k];  // G02
+          r += 2 * G(e, 3, n) * D[j * Nq + j] * D[k * Nq + k];  // G12
+          r *= lam0;
+          r += lam1 * G(e, 6, n);
+          diag[(size_t)e * Np + n] = (T)r;
+        }
+  NRSB_CUDA(cudaMemcpy(o_invDiagA, diag.data(), sizeof(T) * mesh->Nlocal, cudaMemcpyHostToDevice));
+  if ((rc = elliptic->oogs->startFinish<T>(o_invDiagA, 1, 0, gs_op::add, 0, nullptr, elliptic->stream))) return rc;
+  // adyMany: a = 1/a ; masked rows (diag untouched by gs) keep their element value
+  NRSB_CUDA(cudaStreamSynchronize(elliptic->stream));
+  NRSB_CUDA(cudaMemcpy(diag.data(), o_invDiagA, sizeof(T) * mesh->Nlocal, cudaMemcpyDeviceToHost));
+  for (auto& v : diag) v = (T)1 / v;
+  NRSB_CUDA(cudaMemcpy(o_invDiagA, diag.data(), sizeof(T) * mesh->Nlocal, cudaMemcpyHostToDevice));
+  return NRSB_OK;
+}
+template int ellipticBuildDiagonal<double>(elliptic_t*, double*);
+template int ellipticBuildDiagonal<float>(elliptic_t*, float*);
+
+// ------------------------------------------------------------------------------------------
+// setup
+// ------------------------------------------------------------------------------------------
+int elliptic_workspace(elliptic_t* elliptic)
+{
+  int rc;
+  if ((rc = elliptic->redPartials.alloc((size_t)kMaxRedBlocks * kMaxRed))) return rc;
+  if ((rc = elliptic->redTicket.alloc(1))) return rc;
+  elliptic->ws.partials = elliptic->redPartials.p;
+  elliptic->ws.ticket = elliptic->redTicket.p;
+  if (elliptic->comm && elliptic->comm->nranks > 1) elliptic->ws.peer = elliptic->comm->peerReduce();
+  if ((rc = elliptic->o_scal.alloc(S_COUNT))) return rc;
+  if (!elliptic->h_scal) NRSB_CUDA(cudaMallocHost((void**)&elliptic->h_scal, sizeof(double) * S_COUNT));
+  return NRSB_OK;
+}
+
+int ellipticSolveSetup(elliptic_t* elliptic)
+{
+  mesh_t* mesh = elliptic->mesh;
+  options_t& options = elliptic->options;
+  NRSB_REQUIRE(!elliptic->name.empty(), "Empty elliptic solver name!");
+  options.setArgs("DISCRETIZATION", "CONTINUOUS");
+  NRSB_REQUIRE(elliptic->Nfields == 1, "block (Nfields > 1) solves are a 'next' row (SURVEY N3)");
+  // fieldOffset: Nlocal rounded up to ALIGN_SIZE bytes (setup.cpp:295-299, nrssys.hpp:122)
+  if (elliptic->fieldOffset == 0) {
+    const dlong per = 1024 / sizeof(double);
+    elliptic->fieldOffset = ((mesh->Nlocal + per - 1) / per) * per;
+  }
+  int rc;
+  if ((rc = elliptic_workspace(elliptic))) return rc;
+  const size_t fo = (size_t)elliptic->fieldOffset * elliptic->Nfields;
+  if ((rc = elliptic->o_p.alloc(fo))) return rc;
+  if ((rc = elliptic->o_z.alloc(fo))) return rc;
+  if ((rc = elliptic->o_Ap.alloc(fo))) return rc;
+  if ((rc = elliptic->o_x0.alloc(fo))) return rc;
+  if ((rc = elliptic->o_rPfloat.alloc(fo))) return rc;
+  if ((rc = elliptic->o_zPfloat.alloc(fo))) return rc;
+  std::vector<double> l0(1, elliptic->lambda0Value), l1(1, elliptic->lambda1Value);
+  if ((rc = elliptic->o_lambda0.upload(l0))) return rc;
+  if ((rc = elliptic->o_lambda1.upload(l1))) return rc;
+  std::vector<float> l0f(1, (float)elliptic->lambda0Value), l1f(1, (float)elliptic->lambda1Value);
+  if ((rc = elliptic->o_lambda0Pfloat.upload(l0f))) return rc;
+  if ((rc = elliptic->o_lambda1Pfloat.upload(l1f))) return rc;
+
+  // allNeumann (ellipticSetup.cpp:182-204)
+  elliptic->allNeumann = 0;
+  if (elliptic->poisson) {
+    int allNeumann = 1;
+    for (int bc : elliptic->EToB)
+      if (bc > 0 && bc != 4) allNeumann = 0;  // NEUMANN == 4
+    if (elliptic->comm && elliptic->comm->nranks > 1) {
+      std::vector<int> buf(elliptic->comm->nranks, 1);
+      buf[elliptic->comm->rank] = allNeumann;
+      elliptic->comm->allgather_bytes(buf.data(), sizeof(int));
+      for (int v : buf) allNeumann = std::min(allNeumann, v);
+    }
+    elliptic->allNeumann = allNeumann;
+  }
+
+  if ((rc = ellipticOgs(mesh, elliptic->EToB, elliptic))) return rc;
+
+  // ENABLE GS COMM OVERLAP: the reference times both variants and keeps the faster
+  // (ellipticSetup.cpp:278-302).  Splitting only pays when there are halo rows.
+  elliptic->overlap = elliptic->ogs->NhaloGather > 0 && !options.compareArgs("ENABLE GS COMM OVERLAP", "FALSE") &&
+                      mesh->NlocalGatherElements > 0;
+
+  if (options.compareArgs("SOLVER", "PGMRES")) {
+    elliptic->nRestartVectors = 15;
+    options.getArgs("PGMRES RESTART", elliptic->nRestartVectors);
+    NRSB_REQUIRE(elliptic->nRestartVectors >= 1 && elliptic->nRestartVectors <= kMaxRed,
+                 "PGMRES RESTART must be in 1..16");
+    const int m = elliptic->nRestartVectors;
+    const bool flexible = options.compareArgs("SOLVER", "FLEXIBLE");
+    if ((rc = elliptic->o_V.alloc(fo * m))) return rc;
+    if ((rc = elliptic->o_Z.alloc(fo * (flexible ? m : 1)))) return rc;
+    if ((rc = elliptic->o_y.alloc(m))) return rc;
+    elliptic->gmres_H.assign((size_t)(m + 1) * (m + 1), 0.0);
+    elliptic->gmres_sn.assign(m, 0.0);
+    elliptic->gmres_cs.assign(m, 0.0);
+    elliptic->gmres_s.assign(m + 1, 0.0);
+    elliptic->gmres_y.assign(m, 0.0);
+  }
+
+  if ((rc = ellipticPreconditionerSetup(elliptic))) return rc;
+
+  if (options.compareArgs("INITIAL GUESS", "PROJECTION")) {
+    int nVecsProject = 8, nStepsStart = 5;
+    options.getArgs("RESIDUAL PROJECTION VECTORS", nVecsProject);
+    options.getArgs("RESIDUAL PROJECTION START", nStepsStart);
+    const bool aconj = options.compareArgs("INITIAL GUESS", "PROJECTION-ACONJ");
+    elliptic->solutionProjection.reset(new SolutionProjection(elliptic, aconj, nVecsProject, nStepsStart));
+    if ((rc = elliptic->solutionProjection->setup())) return rc;
+  }
+  NRSB_CUDA(cudaDeviceSynchronize());
+  return NRSB_OK;
+}
+
+int ellipticPreconditionerSetup(elliptic_t* elliptic)
+{
+  options_t& options = elliptic->options;
+  elliptic->precon.reset(new precon_t());
+  if (options.compareArgs("PRECONDITIONER", "MULTIGRID")) return ellipticMultiGridSetup(elliptic, elliptic->precon.get());
+  if (options.compareArgs("PRECONDITIONER", "JACOBI")) {
+    int rc;
+    if ((rc = elliptic->precon->o_invDiagA.alloc((size_t)elliptic->fieldOffset * elliptic->Nfields))) return rc;
+    return ellipticBuildDiagonal<double>(elliptic, elliptic->precon->o_invDiagA.p);
+  }
+  if (options.compareArgs("PRECONDITIONER", "NONE") || !options.has("PRECONDITIONER")) {
+    options.setArgs("PRECONDITIONER", "NONE");
+    return NRSB_OK;
+  }
+  set_last_error("unsupported PRECONDITIONER '" + options.getArgs("PRECONDITIONER") +
+                 "' (supported: MULTIGRID, JACOBI, NONE)");
+  return NRSB_ERR_INVALID;
+}
+
+int ellipticPreconditioner(elliptic_t* elliptic, double* o_r, double* o_z)
+{
+  mesh_t* mesh = elliptic->mesh;
+  options_t& options = elliptic->options;
+  precon_t* precon = elliptic->precon.get();
+  const long Nall = (long)elliptic->fieldOffset * elliptic->Nfields;
+  int rc;
+  if (options.compareArgs("PRECONDITIONER", "JACOBI")) {
+    if ((rc = axmyz_launch<double>(mesh->Nlocal, 1.0, o_r, precon->o_invDiagA.p, o_z, elliptic->stream))) return rc;
+  } else if (options.compareArgs("PRECONDITIONER", "MULTIGRID")) {
+    // pfill(z)=0 ; cast r ; V-cycle ; cast z  (ellipticPreconditioner.cpp:57-62)
+    if ((rc = fill_launch<float>(Nall, 0.f, elliptic->o_zPfloat.p, elliptic->stream))) return rc;
+    if ((rc = copy_d2f_launch(Nall, o_r, elliptic->o_rPfloat.p, elliptic->stream))) return rc;
+    if ((rc = precon->MGSolver->Run(elliptic->o_rPfloat.p, elliptic->o_zPfloat.p))) return rc;
+    if ((rc = copy_f2d_launch(Nall, elliptic->o_zPfloat.p, o_z, elliptic->stream))) return rc;
+  } else if (options.compareArgs("PRECONDITIONER", "NONE")) {
+    NRSB_CUDA(cudaMemcpyAsync(o_z, o_r, sizeof(double) * Nall, cudaMemcpyDeviceToDevice, elliptic->stream));
+  } else {
+    set_last_error("Unknown preconditioner");
+    return NRSB_ERR_INVALID;
+  }
+  if (elliptic->allNeumann) return ellipticZeroMean(elliptic, o_z);
+  return NRSB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// PCG (PCG.cpp:85-203)
+// ------------------------------------------------------------------------------------------
+int pcg(elliptic_t* elliptic, double* o_r, double* o_x, double tol, int MAXIT, double& rdotr)
+{
+  mesh_t* mesh = elliptic->mesh;
+  options_t& options = elliptic->options;
+  const bool flexible = options.compareArgs("SOLVER", "FLEXIBLE");
+  const bool precond = !options.compareArgs("PRECONDITIONER", "NONE");
+  cudaStream_t st = elliptic->stream;
+  double* S = elliptic->o_scal.p;
+  double* o_p = elliptic->o_p.p;
+  double* o_z = precond ? elliptic->o_z.p : o_r;
+  double* o_Ap = elliptic->o_Ap.p;
+  const double* o_weight = elliptic->o_invDegree;
+  const long N = mesh->Nlocal;
+  int rc;
+  if ((rc = fill_launch<double>((long)elliptic->fieldOffset * elliptic->Nfields, 0.0, o_p, st))) return rc;
+
+  // rdotr enters as res0Norm = sqrt(sum w r^2 * resNormFactor); without preconditioner the first
+  // rdotz1 is `rdotr` itself (PCG.cpp:131: "rdotz1 = rdotr"), i.e. the NORM, not its square -- a
+  // quirk of the reference that cancels in alpha*p for iteration 1 only through beta = 0; it is
+  // reproduced literally.
+  double h_rdotr = rdotr;
+  NRSB_CUDA(cudaMemcpyAsync(S + S_RDOTR, &h_rdotr, sizeof(double), cudaMemcpyHostToDevice, st));
+  NRSB_CUDA(cudaStreamSynchronize(st));
+
+  int iter = 0;
+  do {
+    iter++;
+    // rdotz2 = rdotz1
+    NRSB_CUDA(cudaMemcpyAsync(S + S_RDOTZ_OLD, S + S_RDOTZ, sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (precond) {
+      if ((rc = ellipticPreconditioner(elliptic, o_r, o_z))) return rc;
+      if ((rc = wdot_launch<double>(N, o_weight, o_r, o_z, S + S_RDOTZ, elliptic->ws, st))) return rc;
+    } else {
+      NRSB_CUDA(cudaMemcpyAsync(S + S_RDOTZ, S + S_RDOTR, sizeof(double), cudaMemcpyDeviceToDevice, st));
+    }
+    DevScalar beta = DevScalar::host(0.0);
+    if (iter > 1) {
+      beta = DevScalar::ratio(S + S_RDOTZ, S + S_RDOTZ_OLD);
+      if (flexible) {
+        if ((rc = wdot_launch<double>(N, o_weight, o_z, o_Ap, S + S_ZDOTAP, elliptic->ws, st))) return rc;
+        // beta = -alpha * zdotAp / rdotz2   (alpha of the previous iteration is still in S_ALPHA)
+        DevScalar b = DevScalar::ratio(S + S_ZDOTAP, S + S_RDOTZ_OLD, -1.0);
+        b.mul = S + S_ALPHA;
+        if ((rc = set_scalar_launch(S + S_BETA, b, st))) return rc;
+        beta = DevScalar::ratio(S + S_BETA, nullptr);
+      }
+    }
+    // p = z + beta p
+    if ((rc = axpby_launch<double>(N, DevScalar::host(1.0), o_z, beta, o_p, st))) return rc;
+    if ((rc = ellipticOperator<double>(elliptic, o_p, o_Ap))) return rc;
+    if ((rc = wdot_launch<double>(N, o_weight, o_p, o_Ap, S + S_PAP, elliptic->ws, st))) return rc;
+    // alpha = rdotz1 / (pAp + 1e-300)
+    if ((rc = set_scalar_launch(S + S_ALPHA, DevScalar::ratio(S + S_RDOTZ, S + S_PAP, 1.0, 1e-300), st))) return rc;
+    DevScalar alpha = DevScalar::ratio(S + S_ALPHA, nullptr);
+    // x += alpha p ; r -= alpha Ap ; rdotr = sum w r^2      (one kernel)
+    if ((rc = update_pcg_launch(N, o_weight, o_Ap, o_p, alpha, o_r, o_x, S + S_NORM, elliptic->ws, st))) return rc;
+    double v;
+    if ((rc = elliptic->read_scalars(S_NORM, 1, &v))) return rc;
+    rdotr = std::sqrt(v * elliptic->resNormFactor);
+    h_rdotr = rdotr;
+    NRSB_CUDA(cudaMemcpyAsync(S + S_RDOTR, &h_rdotr, sizeof(double), cudaMemcpyHostToDevice, st));
+    elliptic->resHistory.push_back(rdotr);
+    if (std::isnan(rdotr)) {
+      set_last_error("Detected invalid resiual norm while running linear solver!");
+      return NRSB_ERR_DIVERGED;
+    }
+  } while (rdotr > tol && iter < MAXIT);
+  elliptic->Niter = iter;
+  return NRSB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// PGMRES (PGMRES.cpp:70-340)
+// ------------------------------------------------------------------------------------------
+static int gmresUpdate(elliptic_t* elliptic, double* o_x, int gmresUpdateSize)
+{
+  const int m = elliptic->nRestartVectors;
+  mesh_t* mesh = elliptic->mesh;
+  std::vector<double>&y = elliptic->gmres_y, &H = elliptic->gmres_H, &s = elliptic->gmres_s;
+  cudaStream_t st = elliptic->stream;
+  const long fo = (long)elliptic->fieldOffset * elliptic->Nfields;
+  for (int k = gmresUpdateSize - 1; k >= 0; --k) {
+    y[k] = s[k];
+    for (int j = k + 1; j < gmresUpdateSize; ++j) y[k] -= H[k + j * (m + 1)] * y[j];
+    y[k] /= H[k + k * (m + 1)];
+  }
+  NRSB_CUDA(cudaMemcpyAsync(elliptic->o_y.p, y.data(), gmresUpdateSize * sizeof(double), cudaMemcpyHostToDevice, st));
+  NRSB_CUDA(cudaStreamSynchronize(st));
+  int rc;
+  if (elliptic->options.compareArgs("SOLVER", "FLEXIBLE"))
+    return update_pgmres_solution_launch(mesh->Nlocal, fo, gmresUpdateSize, elliptic->o_y.p, elliptic->o_Z.p, o_x, st);
+  if ((rc = fill_launch<double>(fo, 0.0, elliptic->o_z.p, st))) return rc;
+  if ((rc = update_pgmres_solution_launch(mesh->Nlocal, fo, gmresUpdateSize, elliptic->o_y.p, elliptic->o_V.p,
+                                          elliptic->o_z.p, st)))
+    return rc;
+  if ((rc = ellipticPreconditioner(elliptic, elliptic->o_z.p, elliptic->o_p.p))) return rc;
+  return axpby_launch<double>(mesh->Nlocal, DevScalar::host(1.0), elliptic->o_p.p, DevScalar::host(1.0), o_x, st);
+}
+
+int pgmres(elliptic_t* elliptic, double* o_r, double* o_x, double tol, int MAXIT, double& rdotr)
+{
+  mesh_t* mesh = elliptic->mesh;
+  cudaStream_t st = elliptic->stream;
+  const int m = elliptic->nRestartVectors;
+  const bool flexible = elliptic->options.compareArgs("SOLVER", "FLEXIBLE");
+  const long fo = (long)elliptic->fieldOffset * elliptic->Nfields;
+  const long N = mesh->Nlocal;
+  double* o_w = elliptic->o_p.p;
+  double* o_Ax = elliptic->o_Ap.p;
+  double* o_V = elliptic->o_V.p;
+  double* o_Z = elliptic->o_Z.p;
+  double* o_b = elliptic->o_z.p;
+  double* S = elliptic->o_scal.p;
+  const double* o_weight = elliptic->o_invDegree;
+  std::vector<double>&y = elliptic->gmres_y, &H = elliptic->gmres_H, &sn = elliptic->gmres_sn, &cs = elliptic->gmres_cs,
+  &s = elliptic->gmres_s;
+  int rc;
+  NRSB_CUDA(cudaMemcpyAsync(o_b, o_r, sizeof(double) * fo, cudaMemcpyDeviceToDevice, st));
+  double nr = rdotr / std::sqrt(elliptic->resNormFactor);
+  double error = rdotr;
+  const double TOL = tol;
+  int iter = 0;
+  for (iter = 0; iter < MAXIT;) {
+    s[0] = nr;
+    // V(:,0) = r/nr
+    if ((rc = axpby_launch<double>(N, DevScalar::host(1.0 / nr), o_r, DevScalar::host(0.0), o_V, st))) return rc;
+    for (int i = 0; i < m; ++i) {
+      double* o_Mv = flexible ? o_Z + (size_t)i * fo : o_Z;
+      if ((rc = ellipticPreconditioner(elliptic, o_V + (size_t)i * fo, o_Mv))) return rc;
+      if ((rc = ellipticOperator<double>(elliptic, o_Mv, o_w))) return rc;
+      // y = V^T w (weighted): stays on the device for the Gram-Schmidt kernel, one copy to the host for H
+      if ((rc = wdot_multi_launch(N, i + 1, fo, o_weight, o_V, o_w, elliptic->o_y.p, elliptic->ws, st))) return rc;
+      if ((rc = gram_schmidt_launch(N, fo, i + 1, o_weight, elliptic->o_y.p, o_V, o_w, S + S_NORM, elliptic->ws, st)))
+        return rc;
+      NRSB_CUDA(cudaMemcpyAsync(S + S_GMRES, elliptic->o_y.p, sizeof(double) * (i + 1), cudaMemcpyDeviceToDevice, st));
+      NRSB_CUDA(cudaMemcpyAsync(S + S_GMRES + (i + 1), S + S_NORM, sizeof(double), cudaMemcpyDeviceToDevice, st));
+      std::vector<double> hv(i + 2);
+      if ((rc = elliptic->read_scalars(S_GMRES, i + 2, hv.data()))) return rc;
+      for (int k = 0; k <= i; ++k) y[k] = hv[k];
+      const double nw = std::sqrt(hv[i + 1]);
+      H[i + 1 + i * (m + 1)] = nw;
+      if (i < m - 1)
+        if ((rc = axpby_launch<double>(N, DevScalar::host(1. / nw), o_w, DevScalar::host(0.0),
+                                       o_V + (size_t)(i + 1) * fo, st)))
+          return rc;
+      for (int k = 0; k <= i; ++k) H[k + i * (m + 1)] = y[k];
+      for (int k = 0; k < i; ++k) {
+        const double h1 = H[k + i * (m + 1)], h2 = H[k + 1 + i * (m + 1)];
+        H[k + i * (m + 1)] = cs[k] * h1 + sn[k] * h2;
+        H[k + 1 + i * (m + 1)] = -sn[k] * h1 + cs[k] * h2;
+      }
+      const double h1 = H[i + i * (m + 1)], h2 = H[i + 1 + i * (m + 1)];
+      const double hr = std::sqrt(h1 * h1 + h2 * h2);
+      cs[i] = h1 / hr;
+      sn[i] = h2 / hr;
+      H[i + i * (m + 1)] = cs[i] * h1 + sn[i] * h2;
+      H[i + 1 + i * (m + 1)] = 0;
+      s[i + 1] = -sn[i] * s[i];
+      s[i] = cs[i] * s[i];
+      iter++;
+      error = std::fabs(s[i + 1]) * std::sqrt(elliptic->resNormFactor);
+      rdotr = error;
+      elliptic->resHistory.push_back(rdotr);
+      if (std::isnan(error)) {
+        set_last_error("Detected invalid resiual norm while running linear solver!");
+        return NRSB_ERR_DIVERGED;
+      }
+      if (error < TOL || iter == MAXIT) {
+        if ((rc = gmresUpdate(elliptic, o_x, i + 1))) return rc;
+        break;
+      }
+    }
+    if (error < TOL || iter == MAXIT) break;
+    if ((rc = gmresUpdate(elliptic, o_x, m))) return rc;
+    if ((rc = ellipticOperator<double>(elliptic, o_x, o_Ax))) return rc;
+    if ((rc = fused_residual_and_norm_launch(N, o_weight, o_b, o_Ax, o_r, S + S_NORM, elliptic->ws, st))) return rc;
+    double v;
+    if ((rc = elliptic->read_scalars(S_NORM, 1, &v))) return rc;
+    nr = std::sqrt(v);
+    error = nr * std::sqrt(elliptic->resNormFactor);
+    rdotr = error;
+    if (error <= TOL) break;
+  }
+  elliptic->Niter = iter;
+  return NRSB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// ellipticSolve (ellipticSolve.cpp:32-190)
+// ------------------------------------------------------------------------------------------
+static int weighted_norm(elliptic_t* elliptic, const double* o_v, double* out)
+{
+  int rc = wnorm2_launch<double>(elliptic->mesh->Nlocal, elliptic->o_invDegree, o_v, elliptic->o_scal.p + S_NORM,
+                                 elliptic->ws, elliptic->stream);
+  if (rc) return rc;
+  double v;
+  if ((rc = elliptic->read_scalars(S_NORM, 1, &v))) return rc;
+  *out = std::sqrt(v) * std::sqrt(elliptic->resNormFactor);
+  return NRSB_OK;
+}
+
+int ellipticSolve(elliptic_t* elliptic, double* o_r, double* o_x)
+{
+  options_t& options = elliptic->options;
+  mesh_t* mesh = elliptic->mesh;
+  cudaStream_t st = elliptic->stream;
+  const long N = mesh->Nlocal;
+  const long fo = (long)elliptic->fieldOffset * elliptic->Nfields;
+  int maxIter = 999;
+  options.getArgs("MAXIMUM ITERATIONS", maxIter);
+  elliptic->resNormFactor = 1 / mesh->volume;
+  elliptic->resHistory.clear();
+  int rc;
+
+  // r = rhs - A x0
+  if ((rc = ellipticAx<double>(elliptic, mesh->Nelements, mesh->o_elementList.p, o_x, elliptic->o_Ap.p))) return rc;
+  if ((rc = axpby_launch<double>(N, DevScalar::host(-1.0), elliptic->o_Ap.p, DevScalar::host(1.0), o_r, st))) return rc;
+  if (elliptic->allNeumann)
+    if ((rc = ellipticZeroMean(elliptic, o_r))) return rc;
+  // mask + gather-scatter of the residual
+  if (elliptic->oogs->ogs->NhaloGather) {
+    if ((rc = ellipticApplyMask<double>(elliptic, o_r))) return rc;
+    if ((rc = elliptic->oogs->startFinish<double>(o_r, elliptic->Nfields, elliptic->fieldOffset, gs_op::add, 0, nullptr,
+                                                  st)))
+      return rc;
+  } else if ((rc = elliptic->oogs->startFinish<double>(o_r, elliptic->Nfields, elliptic->fieldOffset, gs_op::add,
+                                                       elliptic->Nmasked, elliptic->o_maskIds.p, st)))
+    return rc;
+
+  NRSB_CUDA(cudaMemcpyAsync(elliptic->o_x0.p, o_x, sizeof(double) * fo, cudaMemcpyDeviceToDevice, st));
+  if ((rc = fill_launch<double>(fo, 0.0, o_x, st))) return rc;
+  const bool projection = options.compareArgs("INITIAL GUESS", "PROJECTION") && elliptic->solutionProjection;
+  if (projection) {
+    if ((rc = weighted_norm(elliptic, o_r, &elliptic->res00Norm))) return rc;
+    if (std::isnan(elliptic->res00Norm)) {
+      set_last_error(elliptic->name + " unreasonable res00Norm!");
+      return NRSB_ERR_DIVERGED;
+    }
+    if ((rc = elliptic->solutionProjection->pre(o_r))) return rc;
+  }
+  if ((rc = weighted_norm(elliptic, o_r, &elliptic->res0Norm))) return rc;
+  if (std::isnan(elliptic->res0Norm)) {
+    set_last_error(elliptic->name + " unreasonable res00Norm!");
+    return NRSB_ERR_DIVERGED;
+  }
+  double tol = 1e-6;
+  options.getArgs("SOLVER TOLERANCE", tol);
+  if (options.compareArgs("LINEAR SOLVER STOPPING CRITERION", "RELATIVE")) tol *= elliptic->res0Norm;
+
+  elliptic->resNorm = elliptic->res0Norm;
+  if (options.compareArgs("SOLVER", "PCG")) {
+    if ((rc = pcg(elliptic, o_r, o_x, tol, maxIter, elliptic->resNorm))) return rc;
+  } else if (options.compareArgs("SOLVER", "PGMRES")) {
+    if ((rc = pgmres(elliptic, o_r, o_x, tol, maxIter, elliptic->resNorm))) return rc;
+  } else {
+    set_last_error("Linear solver " + options.getArgs("SOLVER") + " is not supported!");
+    return NRSB_ERR_INVALID;
+  }
+  if (projection) {
+    if ((rc = elliptic->solutionProjection->post(o_x))) return rc;
+  } else {
+    elliptic->res00Norm = elliptic->res0Norm;
+  }
+  // x += x0
+  if ((rc = axpby_launch<double>(N, DevScalar::host(1.0), elliptic->o_x0.p, DevScalar::host(1.0), o_x, st))) return rc;
+  if (elliptic->allNeumann)
+    if ((rc = ellipticZeroMean(elliptic, o_x))) return rc;
+  NRSB_CUDA(cudaStreamSynchronize(st));
+  return NRSB_OK;
+}
+
+}  // namespace nrsb

@@ -90,6 +90,10 @@ int add_scalar_launch(long N, DevScalar a, T* x, cudaStream_t s)
 {
   return ew_launch(N, [=] __device__(long i) { x[i] += (T)a.eval(); }, s);
 }
+int set_scalar_launch(double* dst, DevScalar v, cudaStream_t s)
+{
+  return ew_launch(1, [=] __device__(long i) { dst[i] = v.eval(); }, s);
+}
 int copy_d2f_launch(long N, const double* x, float* y, cudaStream_t s)
 {
   return ew_launch(N, [=] __device__(long i) { y[i] = (float)x[i]; }, s);
@@ -137,6 +141,32 @@ int update_pgmres_solution_launch(long N, long offset, int gmresSize, const doub
         double xv = x[i];
         for (int j = 0; j < gmresSize; ++j) xv += Z[i + (size_t)j * offset] * y[j];
         x[i] = xv;
+      },
+      s);
+}
+
+// accumulate.okl / multiScaledAddwOffset.okl (solution projection), Nfields = 1
+int accumulate_launch(long N, int m, long fieldOffset, const double* alpha, const double* x, double* y,
+                      cudaStream_t s)
+{
+  return ew_launch(
+      N,
+      [=] __device__(long n) {
+        double v = alpha[0] * x[n];
+        for (int k = 1; k < m; ++k) v += alpha[k] * x[n + (size_t)k * fieldOffset];
+        y[n] = v;
+      },
+      s);
+}
+int multi_scaled_add_w_offset_launch(long N, int m, long destOffset, long fieldOffset, const double* alphas,
+                                     double beta, double* x, cudaStream_t s)
+{
+  return ew_launch(
+      N,
+      [=] __device__(long n) {
+        double v = x[n + destOffset];
+        for (int k = 0; k < m - 1; ++k) v = -alphas[k] * x[n + (size_t)k * fieldOffset] + beta * v;
+        x[n + destOffset] = v;
       },
       s);
 }

@@ -12,7 +12,8 @@ struct DevScalar {
   double scale = 1.0;
   const double* num = nullptr;
   const double* den = nullptr;
-  double denShift = 0.0;  // value = scale * num / (den + denShift)
+  const double* mul = nullptr;
+  double denShift = 0.0;  // value = scale * num * mul / (den + denShift)
   static DevScalar host(double v)
   {
     DevScalar s;
@@ -32,6 +33,7 @@ struct DevScalar {
   {
     double v = scale;
     if (num) v *= num[0];
+    if (mul) v *= mul[0];
     if (den) v /= (den[0] + denShift);
     return v;
   }
@@ -67,6 +69,7 @@ template <typename T>
 int scale_launch(long N, T a, T* x, cudaStream_t s);
 template <typename T>
 int add_scalar_launch(long N, DevScalar a, T* x, cudaStream_t s);  // x += a
+int set_scalar_launch(double* dst, DevScalar v, cudaStream_t s);  // dst[0] = v
 int copy_d2f_launch(long N, const double* x, float* y, cudaStream_t s);
 int copy_f2d_launch(long N, const float* x, double* y, cudaStream_t s);
 int axmyz_mixed_launch(long N, float a, const double* x, const float* y, double* z, cudaStream_t s);

@@ -1,0 +1,259 @@
+"""Host-side mirror of the reference's elliptic interface (elliptic_t / ellipticSolveSetup /
+ellipticSolve / ellipticOperator / ellipticPreconditioner, src/solvers/elliptic/elliptic.h:185-238)
+over the C ABI.  All numerics run in libnrsb200.so; this module only marshals arguments.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import lib, meshgen
+from .lib import DeviceBuffer, call, vp
+
+
+class _Topo(C.Structure):
+    _fields_ = [("rank", C.c_int), ("nranks", C.c_int), ("nShared", C.c_int64), ("sharedIds", C.c_void_p),
+                ("sharerOffsets", C.c_void_p), ("sharerRanks", C.c_void_p)]
+
+
+class _Config(C.Structure):
+    _fields_ = [("N", C.c_int), ("Nelements", C.c_int32), ("x", C.c_void_p), ("y", C.c_void_p), ("z", C.c_void_p),
+                ("globalIds", C.c_void_p), ("EToB", C.c_void_p), ("topo", C.c_void_p), ("nLevels", C.c_int),
+                ("levelOrders", C.c_void_p), ("levelGlobalIds", C.c_void_p), ("levelTopo", C.c_void_p),
+                ("options", C.c_char_p), ("poisson", C.c_int), ("lambda0", C.c_double), ("lambda1", C.c_double),
+                ("comm", C.c_void_p), ("name", C.c_char_p)]
+
+
+class Topology:
+    """Which global ids of this rank also live on other ranks (what gslib's gs_setup discovers in the
+    reference, ogsSetup.cpp:150-175).  Built by `parallel.discover_topology`."""
+
+    def __init__(self, rank, nranks, shared_ids, sharer_offsets, sharer_ranks):
+        self.shared_ids = np.ascontiguousarray(shared_ids, dtype=np.int64)
+        self.sharer_offsets = np.ascontiguousarray(sharer_offsets, dtype=np.int32)
+        self.sharer_ranks = np.ascontiguousarray(sharer_ranks, dtype=np.int32)
+        self.c = _Topo(rank, nranks, self.shared_ids.size, self.shared_ids.ctypes.data,
+                       self.sharer_offsets.ctypes.data, self.sharer_ranks.ctypes.data)
+
+
+def pressure_options(**kw) -> dict:
+    """Option keys the elliptic path reads, with the reference's pressure defaults
+    (parReader.cpp:836-841,1099) except the coarse solver: BoomerAMG is outside this path, the
+    device Jacobi-PCG stand-in is the default."""
+    o = {
+        "SOLVER": "PGMRES+FLEXIBLE",
+        "PGMRES RESTART": "15",
+        "MAXIMUM ITERATIONS": "200",
+        "SOLVER TOLERANCE": "1e-8",
+        "LINEAR SOLVER STOPPING CRITERION": "RELATIVE",
+        "PRECONDITIONER": "MULTIGRID",
+        "MULTIGRID SMOOTHER": "FOURTHOPTCHEBYSHEV+ASM",
+        "MULTIGRID CHEBYSHEV DEGREE": "3",
+        "MULTIGRID CHEBYSHEV MAX EIGENVALUE BOUND FACTOR": "1.1",
+        "MULTIGRID COARSE SOLVE": "TRUE",
+        "COARSE SOLVER": "JPCG",
+        "COARSE SOLVER TOLERANCE": "1e-3",
+        "COARSE SOLVER MAXIMUM ITERATIONS": "200",
+        "INITIAL GUESS": "PREVIOUS",
+    }
+    o.update({k.upper(): str(v) for k, v in kw.items()})
+    return o
+
+
+def mg_level_orders(options: dict, N: int):
+    """determineMGLevels (MG/determineMGLevels.cpp:58-95)."""
+    sched = options.get("MULTIGRID SCHEDULE", "")
+    if sched:
+        import re
+        return sorted({int(v) for v in re.findall(r"p=(\d+)", sched)}, reverse=True)
+    schwarz = {1: [1], 2: [2, 1], 3: [3, 1], 4: [4, 2, 1], 5: [5, 3, 1], 6: [6, 3, 1], 7: [7, 3, 1], 8: [8, 5, 1],
+               9: [9, 5, 1], 10: [10, 6, 1], 11: [11, 6, 1]}
+    other = {1: [1], 2: [2, 1], 3: [3, 1], 4: [4, 2, 1], 5: [5, 3, 1], 6: [6, 4, 2, 1], 7: [7, 5, 3, 1],
+             8: [8, 6, 4, 1], 9: [9, 7, 5, 1], 10: [10, 8, 5, 1], 11: [11, 9, 5, 1]}
+    sm = options.get("MULTIGRID SMOOTHER", "")
+    return (schwarz if ("ASM" in sm or "RAS" in sm) else other)[N]
+
+
+class Elliptic:
+    """elliptic_t handle."""
+
+    def __init__(self, mesh: meshgen.HexMesh, options: dict, *, comm=None, topo_of=None, poisson=True, lambda0=1.0,
+                 lambda1=0.0, name="pressure"):
+        self.mesh = mesh
+        self.options = dict(options)
+        self.N, self.Np = mesh.N, mesh.Np
+        self.Nlocal = mesh.Nelements * mesh.Np
+        self._keep = []
+        opt_txt = "\n".join("%s=%s" % kv for kv in self.options.items()).encode()
+        levels = []
+        if "MULTIGRID" in self.options.get("PRECONDITIONER", ""):
+            levels = [n for n in mg_level_orders(self.options, mesh.N) if n != mesh.N]
+        lvl_ids = [np.ascontiguousarray(meshgen.global_ids_at_order(mesh, n)) for n in levels]
+        orders = np.array(levels, dtype=np.int32)
+        id_ptrs = (C.c_void_p * max(len(levels), 1))(*[a.ctypes.data for a in lvl_ids])
+        topo = topo_of(mesh.global_ids) if topo_of else None
+        lvl_topos = [topo_of(a) for a in lvl_ids] if topo_of else []
+        topo_ptrs = (C.c_void_p * max(len(levels), 1))(*[C.addressof(t.c) for t in lvl_topos]) if lvl_topos else None
+        x, y, z = (np.ascontiguousarray(a, dtype=np.float64) for a in (mesh.x, mesh.y, mesh.z))
+        gid = np.ascontiguousarray(mesh.global_ids, dtype=np.int64)
+        etob = np.ascontiguousarray(mesh.EToB, dtype=np.int32)
+        self._keep += [x, y, z, gid, etob, orders, lvl_ids, id_ptrs, topo, lvl_topos, topo_ptrs, opt_txt]
+        cfg = _Config(mesh.N, mesh.Nelements, x.ctypes.data, y.ctypes.data, z.ctypes.data, gid.ctypes.data,
+                      etob.ctypes.data, C.addressof(topo.c) if topo else None, len(levels),
+                      orders.ctypes.data if len(levels) else None,
+                      C.cast(id_ptrs, C.c_void_p) if len(levels) else None,
+                      C.cast(topo_ptrs, C.c_void_p) if topo_ptrs is not None else None, opt_txt,
+                      1 if poisson else 0, lambda0, lambda1, comm.handle if comm is not None else None,
+                      name.encode())
+        self._h = C.c_void_p()
+        call("nrsb_elliptic_setup", C.byref(cfg), C.byref(self._h))
+        self.fieldOffset = self.get_int("fieldOffset")
+        self.Nmasked = self.get_int("Nmasked")
+        self.Niter = 0
+        self.res00Norm = self.res0Norm = self.resNorm = 0.0
+
+    # ---- properties
+    def get_int(self, key) -> int:
+        v = C.c_int64(0)
+        call("nrsb_elliptic_get_int", self._h, key.encode(), C.byref(v))
+        return v.value
+
+    def get_real(self, key) -> float:
+        v = C.c_double(0)
+        call("nrsb_elliptic_get_real", self._h, key.encode(), C.byref(v))
+        return v.value
+
+    def get_array(self, key, dtype) -> np.ndarray:
+        n = C.c_int64(0)
+        call("nrsb_elliptic_get_array", self._h, key.encode(), None, C.c_int64(0), C.byref(n))
+        out = np.zeros(n.value, dtype=dtype)
+        if n.value:
+            call("nrsb_elliptic_get_array", self._h, key.encode(), vp(out), C.c_int64(n.value), C.byref(n))
+        return out
+
+    def set_option(self, key, value):
+        call("nrsb_elliptic_set_option", self._h, key.encode(), str(value).encode())
+        self.options[key.upper()] = str(value).upper()
+
+    def set_ax_variant(self, precision, variant):
+        call("nrsb_elliptic_set_ax_variant", self._h, C.c_int(precision), C.c_int(variant))
+
+    def autotune(self):
+        a, b = C.c_int(-1), C.c_int(-1)
+        call("nrsb_elliptic_autotune", self._h, C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    # ---- the reference's entry points
+    def solve(self, o_r: DeviceBuffer, o_x: DeviceBuffer):
+        """ellipticSolve(elliptic, o_r, o_x)."""
+        it = C.c_int(0)
+        r00, r0, r = C.c_double(0), C.c_double(0), C.c_double(0)
+        call("nrsb_elliptic_solve", self._h, vp(o_r), vp(o_x), C.byref(it), C.byref(r00), C.byref(r0), C.byref(r))
+        self.Niter, self.res00Norm, self.res0Norm, self.resNorm = it.value, r00.value, r0.value, r.value
+        return self.Niter
+
+    def solve_host(self, rhs: np.ndarray, x: np.ndarray):
+        it = C.c_int(0)
+        r00, r0, r = C.c_double(0), C.c_double(0), C.c_double(0)
+        call("nrsb_elliptic_solve_host", self._h, vp(rhs), vp(x), C.byref(it), C.byref(r00), C.byref(r0),
+             C.byref(r))
+        self.Niter, self.res00Norm, self.res0Norm, self.resNorm = it.value, r00.value, r0.value, r.value
+        return self.Niter
+
+    def operator(self, o_q, o_Aq, *, level=0, precision=8, masked=True):
+        """ellipticOperator(elliptic, o_q, o_Aq, precision, masked)."""
+        call("nrsb_elliptic_operator", self._h, C.c_int(level), C.c_int(precision), vp(o_q), vp(o_Aq),
+             C.c_int(1 if masked else 0))
+
+    def operator_host(self, q: np.ndarray, Aq: np.ndarray):
+        call("nrsb_elliptic_operator_host", self._h, vp(q), vp(Aq))
+
+    def ax(self, o_q, o_Aq, *, level=0, precision=8):
+        call("nrsb_elliptic_ax", self._h, C.c_int(level), C.c_int(precision), vp(o_q), vp(o_Aq))
+
+    def preconditioner(self, o_r, o_z):
+        call("nrsb_elliptic_preconditioner", self._h, vp(o_r), vp(o_z))
+
+    def level_op(self, level, op, o_in, o_out):
+        call("nrsb_elliptic_level_op", self._h, C.c_int(level), op.encode(), vp(o_in), vp(o_out))
+
+    def res_history(self):
+        return self.get_array("resHistory", np.float64)
+
+    def destroy(self):
+        if self._h:
+            call("nrsb_elliptic_destroy", self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+class OperatorBench:
+    """The fused operator  Aq = Q Q^T mask (A q)  on a box brick per rank: what bench.py times."""
+
+    def __init__(self, N, nel_per_rank, *, rank=0, nranks=1, dist=None, seed=1234):
+        from . import parallel
+        self.proc_grid = meshgen.brick_partition(nranks)
+        nel = tuple(n * p for n, p in zip(nel_per_rank, self.proc_grid))
+        self.mesh = meshgen.box_mesh(N, nel, rank=rank, nranks=nranks)
+        self.comm = parallel.Comm(dist) if nranks > 1 else None
+        topo_of = (lambda ids: parallel.discover_topology(ids, self.comm)) if nranks > 1 else None
+        opts = {"SOLVER": "PCG", "PRECONDITIONER": "NONE", "MAXIMUM ITERATIONS": "100", "SOLVER TOLERANCE": "1e-12"}
+        self.elliptic = Elliptic(self.mesh, opts, comm=self.comm, topo_of=topo_of)
+        self.Nelements, self.Np = self.mesh.Nelements, self.mesh.Np
+        fo = self.elliptic.fieldOffset
+        r = np.random.Generator(np.random.PCG64(seed + rank))
+        self.h_q = lib.PinnedBuffer(fo, np.float64)
+        self.h_Aq = lib.PinnedBuffer(fo, np.float64)
+        self.h_q.array[:] = 0
+        self.h_q.array[:self.Nelements * self.Np] = r.random(self.Nelements * self.Np)
+        self.d_q = DeviceBuffer(like=self.h_q.array)
+        self.d_Aq = DeviceBuffer.zeros(fo, np.float64)
+        self.ax_variant = self.elliptic.autotune()[0]
+        self.launches_per_step = 2 if nranks == 1 else (4 if self.elliptic.get_int("overlap") else 4)
+        self._ev = [lib.Event() for _ in range(3)]
+
+    def step(self):
+        self.elliptic.operator(self.d_q, self.d_Aq)
+
+    def timed_step(self, flush=True):
+        """(ms for the whole operator, ms for the axhelm launch alone)."""
+        if flush:
+            lib.l2_flush()
+        e0, e1, e2 = self._ev
+        e0.record()
+        self.elliptic.operator(self.d_q, self.d_Aq)
+        e1.record()
+        e1.synchronize()
+        total = e0.elapsed_ms(e1)
+        # axhelm alone, same cold-L2 conditions
+        if flush:
+            lib.l2_flush()
+        e0.record()
+        self.elliptic.ax(self.d_q, self.d_Aq)
+        e2.record()
+        e2.synchronize()
+        return total, e0.elapsed_ms(e2)
+
+    def e2e_step(self):
+        e0, e1, _ = self._ev
+        e0.record()
+        self.elliptic.operator_host(self.h_q.array, self.h_Aq.array)
+        e1.record()
+        e1.synchronize()
+        return e0.elapsed_ms(e1)
+
+    def ncu_traffic_bytes(self):
+        """dram bytes per axhelm launch from the committed ncu capture (profiles/), or None."""
+        import json
+        import os
+        p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "ncu_traffic.json")
+        try:
+            return json.load(open(p)).get("axhelm_fp64_N7_E4096_dram_bytes")
+        except Exception:
+            return None

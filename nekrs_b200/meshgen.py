@@ -204,3 +204,22 @@ def box_mesh(N: int, nel, *, kershaw_eps: float | None = None, rank: int = 0, nr
 def kershaw_rhs(mesh: HexMesh) -> np.ndarray:
     """f = 3 pi^2 sin(pi x) sin(pi y) sin(pi z)   (kershaw.udf:20-23)."""
     return 3 * np.pi ** 2 * np.sin(np.pi * mesh.x) * np.sin(np.pi * mesh.y) * np.sin(np.pi * mesh.z)
+
+
+def global_ids_at_order(mesh: HexMesh, Nc: int) -> np.ndarray:
+    """C0 numbering of the same elements at polynomial order Nc (the numbering nek's set_glo_num
+    gives the level mesh created by createMeshMG, meshSetup.cpp:293-348)."""
+    nx, ny, nz = mesh.nel_global
+    x0, y0, z0 = mesh.brick_lo
+    ex, ey, ez = mesh.brick_n
+    iz, iy, ix = np.meshgrid(np.arange(z0, z0 + ez), np.arange(y0, y0 + ey), np.arange(x0, x0 + ex), indexing="ij")
+    ix, iy, iz = ix.ravel(), iy.ravel(), iz.ravel()
+    Nq = Nc + 1
+    li = np.arange(Nq)
+    kk, jj, ii = np.meshgrid(li, li, li, indexing="ij")
+    ii, jj, kk = ii.ravel(), jj.ravel(), kk.ravel()
+    NX, NY = nx * Nc + 1, ny * Nc + 1
+    gi = ix[:, None] * Nc + ii[None, :]
+    gj = iy[:, None] * Nc + jj[None, :]
+    gk = iz[:, None] * Nc + kk[None, :]
+    return (1 + gi + NX * (gj + NY * gk)).astype(np.int64).ravel()

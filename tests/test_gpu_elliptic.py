@@ -1,0 +1,244 @@
+"""GPU parity of the solver-level path (ellipticSolveSetup / ellipticOperator / ellipticSolve with PCG,
+PGMRES, Jacobi and p-multigrid preconditioners) against the oracle driver (oracle/driver.py = the
+reference's host control flow over the restated serial kernels), through the C ABI.
+
+Tolerances: fp64 operator 1e-12; per-iteration residual norms 1e-10 in the first iterations (round-off
+from FMA contraction / summation order is amplified by the Krylov recurrences afterwards); fp32
+multigrid kernels 1e-5; iteration counts +-1 (BASELINE.json north_star).
+"""
+import numpy as np
+import pytest
+
+from nekrs_b200 import lib, meshgen
+from nekrs_b200.elliptic import Elliptic, pressure_options
+from nekrs_b200.lib import DeviceBuffer as DB
+from oracle import driver
+
+pytestmark = pytest.mark.gpu
+
+
+def relerr(a, b):
+    return np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300)
+
+
+def padded(v, n):
+    out = np.zeros(n)
+    out[:v.size] = v
+    return out
+
+
+@pytest.fixture(scope="module")
+def case_bp5(orc):
+    mesh = meshgen.box_mesh(7, (3, 3, 2), kershaw_eps=0.3)
+    opts = {"SOLVER": "PCG", "PRECONDITIONER": "NONE", "MAXIMUM ITERATIONS": "60", "SOLVER TOLERANCE": "1e-15"}
+    ell = Elliptic(mesh, opts)
+    ref = driver.OSolver(mesh, opts, orc)
+    return mesh, ell, ref
+
+
+def test_setup_maps_bit_exact(case_bp5):
+    mesh, ell, ref = case_bp5
+    assert np.array_equal(ell.get_array("maskIds", np.int32), ref.ell.mask_ids)      # Dirichlet ids
+    assert np.array_equal(ell.get_array("invDegree", np.float64), ref.ell.inv_degree)
+    assert np.array_equal(ell.get_array("meshInvDegree", np.float64), ref.mesh.ogs.inv_degree)
+    assert abs(ell.get_real("volume") - ref.mesh.volume) < 1e-13
+    assert relerr(ell.get_array("ggeo", np.float64), ref.mesh.ggeo.ravel()) < 1e-12
+    assert relerr(ell.get_array("D", np.float64), ref.mesh.D.ravel()) < 1e-13
+    assert ell.get_int("allNeumann") == 0 and ref.ell.allNeumann == 0
+    assert ell.fieldOffset == ref.fieldOffset
+
+
+def test_operator_fp64(case_bp5):
+    mesh, ell, ref = case_bp5
+    n = mesh.Nelements * mesh.Np
+    q = np.random.Generator(np.random.PCG64(3)).random(n)
+    out_ref = np.zeros(n)
+    ref.ell.operator(q, out_ref)
+    d_q, d_Aq = DB(like=padded(q, ell.fieldOffset)), DB.zeros(ell.fieldOffset, np.float64)
+    ell.operator(d_q, d_Aq)
+    assert relerr(d_Aq.download()[:n], out_ref) < 1e-12
+    # host-buffer entry point
+    Aq = np.zeros(n)
+    ell.operator_host(q, Aq)
+    assert relerr(Aq, out_ref) < 1e-12
+    # every autotuned variant gives the same answer (benchmarkAx.cpp:289-305: 400 eps)
+    for v in (0, 1, 2, 3):
+        ell.set_ax_variant(8, v)
+        ell.operator(d_q, d_Aq)
+        assert relerr(d_Aq.download()[:n], out_ref) < 400 * np.finfo(np.float64).eps
+    ell.set_ax_variant(8, -1)
+
+
+def test_bp5_pcg_residual_history(case_bp5):
+    mesh, ell, ref = case_bp5
+    n = mesh.Nelements * mesh.Np
+    rhs = meshgen.kershaw_rhs(mesh)
+    x_ref = ref.solve(rhs, np.zeros(n))
+    d_r, d_x = DB(like=padded(rhs, ell.fieldOffset)), DB.zeros(ell.fieldOffset, np.float64)
+    it = ell.solve(d_r, d_x)
+    assert it == ref.Niter == 60          # tol 1e-15 is never reached: fixed work (kershaw.udf:47-53)
+    h, hr = ell.res_history(), np.array(ref.res_history)
+    assert abs(ell.res0Norm - ref.res0Norm) / ref.res0Norm < 1e-13
+    assert np.max(np.abs(h[:5] - hr[:5]) / hr[:5]) < 1e-10
+    assert np.max(np.abs(h - hr) / hr) < 1e-6
+    assert relerr(d_x.download()[:n], x_ref) < 1e-7
+
+
+@pytest.mark.parametrize("solver", ["PCG", "PCG+FLEXIBLE", "PGMRES", "PGMRES+FLEXIBLE"])
+def test_jacobi_preconditioned_solvers(orc, solver):
+    mesh = meshgen.box_mesh(5, (3, 2, 2), kershaw_eps=0.5)
+    opts = {"SOLVER": solver, "PRECONDITIONER": "JACOBI", "MAXIMUM ITERATIONS": "300", "SOLVER TOLERANCE": "1e-8",
+            "LINEAR SOLVER STOPPING CRITERION": "RELATIVE", "PGMRES RESTART": "12"}
+    ell = Elliptic(mesh, opts)
+    ref = driver.OSolver(mesh, opts, orc)
+    n = mesh.Nelements * mesh.Np
+    rhs = meshgen.kershaw_rhs(mesh)
+    x_ref = ref.solve(rhs, np.zeros(n))
+    x = np.zeros(n)
+    it = ell.solve_host(rhs, x)
+    assert abs(it - ref.Niter) <= 1
+    k = min(len(ref.res_history), it, 8)
+    h, hr = ell.res_history(), np.array(ref.res_history)
+    assert np.max(np.abs(h[:k] - hr[:k]) / hr[:k]) < 1e-9
+    assert ell.resNorm <= 1e-8 * ell.res0Norm * 1.0000001
+    assert relerr(x, x_ref) < 1e-6
+    # discretisation check: u = sin sin sin solves -lap u = 3 pi^2 u only in weak form with the mass matrix;
+    # here the rhs is the udf's pointwise P0 (kershaw.udf:20-23), so only solver parity is asserted.
+
+
+def _mg_case(orc, N, nel, smoother, extra=None, eps=0.3):
+    mesh = meshgen.box_mesh(N, nel, kershaw_eps=eps)
+    opts = pressure_options(**{"MULTIGRID SMOOTHER": smoother})
+    if extra:
+        opts.update(extra)
+    ell = Elliptic(mesh, opts)
+    ref = driver.OSolver(mesh, opts, orc)
+    return mesh, opts, ell, ref
+
+
+@pytest.mark.parametrize("smoother", ["FOURTHOPTCHEBYSHEV+RAS", "FOURTHOPTCHEBYSHEV+ASM", "CHEBYSHEV+DAMPEDJACOBI"])
+def test_multigrid_setup_and_components(orc, smoother):
+    mesh, opts, ell, ref = _mg_case(orc, 7, (2, 2, 2), smoother)
+    nl = ell.get_int("nLevels")
+    assert nl == len(ref.levels)
+    rng = np.random.Generator(np.random.PCG64(11))
+    for k in range(nl):
+        L = ref.levels[k]
+        assert ell.get_int("level%d:N" % k) == L.degree
+        assert np.array_equal(ell.get_array("level%d:maskIds" % k, np.int32), L.ell.mask_ids)
+        assert np.array_equal(ell.get_array("level%d:invDegree" % k, np.float64), L.ell.inv_degree)
+        if not L.has_smoother:
+            continue
+        # lambda_max estimate of S*A: same Arnoldi, fp32 operator inside -> 1e-4
+        assert abs(ell.get_real("level%d:maxEig" % k) - L.max_eig_value) / L.max_eig_value < 2e-4
+        n = L.Nrows
+        u = rng.random(n).astype(np.float32)
+        u[L.ell.mask_ids] = 0
+        if "DAMPEDJACOBI" not in smoother:
+            ref_out = np.zeros(n, np.float32)
+            L.schwarz.smooth(u.copy(), ref_out)
+            d_out = DB.zeros(n, np.float32)
+            ell.level_op(k, "smoothSchwarz", DB(like=u), d_out)
+            # S Lambda^-1 S^T is invariant to the eigenvector sign/basis choice: compare outputs, not Sx
+            assert relerr(d_out.download(), ref_out) < 2e-5
+        # fp32 operator of the level
+        ref_Au = np.zeros(n, np.float32)
+        L.ell.operator(u, ref_Au)
+        d_Au = DB.zeros(n, np.float32)
+        ell.operator(DB(like=u), d_Au, level=k, precision=4)
+        assert relerr(d_Au.download(), ref_Au) < 1e-5
+        # full smoother application (Chebyshev), down leg
+        rhs = rng.random(n).astype(np.float32)
+        rhs[L.ell.mask_ids] = 0
+        ref_x = np.zeros(n, np.float32)
+        # use the oracle's own lambda for the oracle and the product's for the product: they agree to 2e-4
+        L.smooth(rhs.copy(), ref_x, True)
+        d_x = DB.zeros(n, np.float32)
+        ell.level_op(k, "smooth", DB(like=rhs), d_x)
+        assert relerr(d_x.download(), ref_x) < 5e-4
+
+
+@pytest.mark.parametrize("N,nel,smoother,extra", [
+    (7, (3, 3, 3), "FOURTHOPTCHEBYSHEV+RAS", None),                       # kershaw.par:16 (BPS5 setting)
+    (7, (2, 2, 2), "FOURTHOPTCHEBYSHEV+ASM", None),                       # pressure default, parReader.cpp:839
+    (5, (3, 2, 2), "CHEBYSHEV+DAMPEDJACOBI", {"SOLVER": "PCG+FLEXIBLE"}),
+    (3, (4, 4, 4), "FOURTHOPTCHEBYSHEV+RAS", {"MULTIGRID COARSE SOLVE": "FALSE", "COARSE SOLVER": "SMOOTHER"}),
+    (7, (2, 2, 2), "FOURTHCHEBYSHEV+ASM", {"MULTIGRID COARSE SOLVE AND SMOOTH": "TRUE"}),
+])
+def test_bps5_iteration_parity(orc, N, nel, smoother, extra):
+    mesh, opts, ell, ref = _mg_case(orc, N, nel, smoother, extra)
+    n = mesh.Nelements * mesh.Np
+    rhs = meshgen.kershaw_rhs(mesh)
+    x_ref = ref.solve(rhs, np.zeros(n))
+    x = np.zeros(n)
+    it = ell.solve_host(rhs, x)
+    assert abs(it - ref.Niter) <= 1, (it, ref.Niter)
+    assert it < int(opts["MAXIMUM ITERATIONS"])
+    h, hr = ell.res_history(), np.array(ref.res_history)
+    k = min(len(h), len(hr), 4)
+    assert np.max(np.abs(h[:k] - hr[:k]) / hr[:k]) < 5e-3      # fp32 V-cycle inside
+    assert ell.resNorm <= 1e-8 * ell.res0Norm * 1.0000001
+    assert relerr(x, x_ref) < 1e-6
+
+
+def test_preconditioner_vcycle_output(orc):
+    mesh, opts, ell, ref = _mg_case(orc, 7, (2, 2, 2), "FOURTHOPTCHEBYSHEV+RAS")
+    n = mesh.Nelements * mesh.Np
+    r = np.random.Generator(np.random.PCG64(5)).random(n)
+    r[ref.ell.mask_ids] = 0
+    ref.orc.gs_add(ref.ell.ogs, r)
+    z_ref = np.zeros(n)
+    ref.preconditioner(r, z_ref)
+    d_z = DB.zeros(ell.fieldOffset, np.float64)
+    ell.preconditioner(DB(like=padded(r, ell.fieldOffset)), d_z)
+    assert relerr(d_z.download()[:n], z_ref) < 2e-4
+    assert abs(ell.get_int("coarseIterations") - ref.coarse.last_iter) <= 8
+
+
+def test_solution_projection(orc):
+    mesh = meshgen.box_mesh(5, (2, 2, 2), kershaw_eps=0.4)
+    opts = {"SOLVER": "PCG", "PRECONDITIONER": "JACOBI", "MAXIMUM ITERATIONS": "300", "SOLVER TOLERANCE": "1e-9",
+            "LINEAR SOLVER STOPPING CRITERION": "RELATIVE", "INITIAL GUESS": "PROJECTION-ACONJ",
+            "RESIDUAL PROJECTION VECTORS": "4", "RESIDUAL PROJECTION START": "1"}
+    ell = Elliptic(mesh, opts)
+    ref = driver.OSolver(mesh, opts, orc)
+    n = mesh.Nelements * mesh.Np
+    base = meshgen.kershaw_rhs(mesh)
+    iters = []
+    for step in range(6):   # slowly varying right-hand sides: projection cuts the iteration count
+        rhs = base * (1.0 + 0.05 * step) + 0.01 * step * np.cos(3 * mesh.x)
+        x_ref = ref.solve(rhs, np.zeros(n))
+        x = np.zeros(n)
+        it = ell.solve_host(rhs, x)
+        iters.append((it, ref.Niter))
+        assert abs(it - ref.Niter) <= 1
+        assert relerr(x, x_ref) < 1e-6
+    assert iters[-1][0] < iters[0][0]
+
+
+def test_all_neumann_null_space(orc):
+    mesh = meshgen.box_mesh(3, (3, 3, 2), bc=meshgen.NEUMANN)
+    opts = {"SOLVER": "PCG", "PRECONDITIONER": "JACOBI", "MAXIMUM ITERATIONS": "200", "SOLVER TOLERANCE": "1e-8",
+            "LINEAR SOLVER STOPPING CRITERION": "RELATIVE"}
+    ell = Elliptic(mesh, opts)
+    ref = driver.OSolver(mesh, opts, orc)
+    assert ell.get_int("allNeumann") == 1 and ell.Nmasked == 0
+    n = mesh.Nelements * mesh.Np
+    rhs = np.cos(2 * np.pi * mesh.x) * np.cos(2 * np.pi * mesh.y)
+    x_ref = ref.solve(rhs, np.zeros(n))
+    x = np.zeros(n)
+    it = ell.solve_host(rhs, x)
+    assert abs(it - ref.Niter) <= 1
+    assert abs(x.sum()) / n < 1e-12          # ellipticZeroMean
+    assert relerr(x, x_ref) < 1e-6
+
+
+def test_error_codes():
+    mesh = meshgen.box_mesh(3, (2, 2, 2))
+    with pytest.raises(lib.NrsbError) as e:
+        Elliptic(mesh, {"SOLVER": "PCG", "PRECONDITIONER": "SEMFEM"})
+    assert e.value.code == -1 and "PRECONDITIONER" in str(e.value)
+    ell = Elliptic(mesh, {"SOLVER": "BICGSTAB", "PRECONDITIONER": "NONE"})
+    n = ell.fieldOffset
+    with pytest.raises(lib.NrsbError):
+        ell.solve(DB.zeros(n, np.float64), DB.zeros(n, np.float64))
