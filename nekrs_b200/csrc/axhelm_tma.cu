@@ -1,0 +1,317 @@
+// axhelm_tma.cu -- persistent, warp-specialised axhelm for Nq = 8 (N = 7): the element slabs
+// (q: 1 plane set, ggeo: 6 or 7 planes) are streamed into a shared-memory ring by ONE producer
+// lane with bulk async copies (cp.async.bulk ... mbarrier::complete_tx, the TMA engine's 1-D path),
+// while groups of Nq^2 consumer threads each work on one element with the pencil algorithm of
+// axhelm.inc (variant 1).  One CTA per SM, grid = #SMs: per-SM bytes in flight are set by the ring
+// depth (NSTAGES x 28 KB), not by occupancy, and the tail is at most one element per group.
+//
+// Why: at E = 4096 the non-persistent kernels lose ~30 % to wave quantisation (4096 blocks over
+// 148 x 8 slots) and to the load -> compute -> store phases of each short-lived block; the ring
+// keeps HBM busy through all phases (ncu of variant 1: DRAM 43 %, occupancy-limited).
+//
+// Same arithmetic order as variant 1 => identical results.
+#include "common.cuh"
+
+namespace nrsb {
+
+namespace {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void group_sync(int id, int nthreads)
+{
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+template <typename T, int Nq>
+struct SlabT {
+  static constexpr int bankMod = 32 / (sizeof(T) / 4);
+  static constexpr int plane()
+  {
+    int p = Nq * Nq;
+    while (p % bankMod != Nq % bankMod) ++p;
+    return p;
+  }
+  static constexpr int P = plane();
+  static constexpr int size = P * Nq;
+  __device__ static __forceinline__ int rot(int i, int j)
+  {
+    int r = i + j;
+    return r >= Nq ? r - Nq : r;
+  }
+  __device__ static __forceinline__ int idx(int i, int j, int k) { return rot(i, j) + Nq * j + P * k; }
+};
+
+}  // namespace
+
+template <typename T, int Nq, int NGROUPS, int NSTAGES, bool kPoisson>
+__global__ void __launch_bounds__(NGROUPS* Nq* Nq + 32, 1)
+    ax_tma_kernel(const dlong Nelements, const dlong* __restrict__ elementList, const T* __restrict__ ggeo,
+                  const DMat<T, Nq> Dm, const T* __restrict__ lambda0, const T* __restrict__ lambda1,
+                  const T* __restrict__ q, T* __restrict__ Aq)
+{
+  constexpr int Np = Nq * Nq * Nq;
+  constexpr int Nq2 = Nq * Nq;
+  constexpr int NG = kPoisson ? 6 : 7;  // geometric-factor planes needed (G00..G22 [, GwJ]); contiguous
+  constexpr uint32_t gBytes = NG * Np * sizeof(T);
+  constexpr uint32_t qBytes = Np * sizeof(T);
+  constexpr int stageElems = (NG + 1) * Np;
+  static_assert(NSTAGES % NGROUPS == 0, "each consumer group must own a private sub-ring");
+  using S = SlabT<T, Nq>;
+
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  T* stages = reinterpret_cast<T*>(smem_raw);                        // [NSTAGES][(NG+1)*Np]
+  T* work = stages + (size_t)NSTAGES * stageElems;                   // [NGROUPS][3][S::size]
+  uint64_t* full = reinterpret_cast<uint64_t*>(work + (size_t)NGROUPS * 3 * S::size);
+  uint64_t* empty = full + NSTAGES;
+
+  const int tid = threadIdx.x;
+  constexpr int nConsumers = NGROUPS * Nq2;
+  const int myCount = (Nelements > (dlong)blockIdx.x) ? (int)((Nelements - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+
+  if (tid == 0) {
+    for (int s = 0; s < NSTAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], Nq2);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (tid >= nConsumers) {
+    // ===== producer warp: one lane streams element slabs into the ring =====
+    if (tid == nConsumers) {
+      for (int i = 0; i < myCount; ++i) {
+        const int s = i % NSTAGES;
+        if (i >= NSTAGES) mbar_wait(&empty[s], ((i / NSTAGES) - 1) & 1);
+        const dlong element = elementList[blockIdx.x + (dlong)i * gridDim.x];
+        T* st = stages + (size_t)s * stageElems;
+        mbar_expect_tx(&full[s], gBytes + qBytes);
+        bulk_g2s(st, ggeo + (size_t)element * 7 * Np, gBytes, &full[s]);
+        bulk_g2s(st + NG * Np, q + (size_t)element * Np, qBytes, &full[s]);
+      }
+    }
+    return;
+  }
+
+  // ===== consumers: group g owns elements g, g+NGROUPS, ... of this CTA =====
+  const int g = tid / Nq2;
+  const int t = tid % Nq2;
+  const int a = t % Nq;
+  const int b = t / Nq;
+  T* su = work + (size_t)g * 3 * S::size;
+  T* sr = su + S::size;
+  T* ss = sr + S::size;
+  const int tbase = S::rot(a, b) + Nq * b;
+  const T lam0 = lambda0[0];
+  const T lam1 = kPoisson ? T(0) : lambda1[0];
+
+  for (int i = g; i < myCount; i += NGROUPS) {
+    const int s = i % NSTAGES;
+    const dlong element = elementList[blockIdx.x + (dlong)i * gridDim.x];
+    const T* st = stages + (size_t)s * stageElems;
+    const T* sq = st + NG * Np;
+    mbar_wait(&full[s], (i / NSTAGES) & 1);
+
+    // 1. q in the t-layout + swizzled copy
+    T r_q[Nq];
+#pragma unroll
+    for (int k = 0; k < Nq; ++k) r_q[k] = sq[t + Nq2 * k];
+#pragma unroll
+    for (int k = 0; k < Nq; ++k) su[tbase + S::P * k] = r_q[k];
+    group_sync(1 + g, Nq2);
+
+    // 2. derivatives along the owned pencils
+    T r_qt[Nq];
+#pragma unroll
+    for (int k = 0; k < Nq; ++k) {
+      T v = 0;
+#pragma unroll
+      for (int m = 0; m < Nq; ++m) v += Dm.v[k * Nq + m] * r_q[m];
+      r_qt[k] = v;
+    }
+    {
+      T u[Nq];
+#pragma unroll
+      for (int m = 0; m < Nq; ++m) u[m] = su[S::idx(m, a, b)];
+#pragma unroll
+      for (int ii = 0; ii < Nq; ++ii) {
+        T v = 0;
+#pragma unroll
+        for (int m = 0; m < Nq; ++m) v += Dm.v[ii * Nq + m] * u[m];
+        sr[S::idx(ii, a, b)] = v;
+      }
+#pragma unroll
+      for (int m = 0; m < Nq; ++m) u[m] = su[S::idx(a, m, b)];
+#pragma unroll
+      for (int jj = 0; jj < Nq; ++jj) {
+        T v = 0;
+#pragma unroll
+        for (int m = 0; m < Nq; ++m) v += Dm.v[jj * Nq + m] * u[m];
+        ss[S::idx(a, jj, b)] = v;
+      }
+    }
+    group_sync(1 + g, Nq2);
+
+    // 3. geometric factors from the staged slab (t-layout: conflict-free)
+    T r_mass[kPoisson ? 1 : Nq];
+#pragma unroll
+    for (int k = 0; k < Nq; ++k) {
+      const int n = t + Nq2 * k;
+      const T G00 = st[0 * Np + n], G01 = st[1 * Np + n], G11 = st[2 * Np + n];
+      const T G12 = st[3 * Np + n], G02 = st[4 * Np + n], G22 = st[5 * Np + n];
+      if constexpr (!kPoisson) r_mass[k] = st[6 * Np + n] * lam1 * r_q[k];
+      const int p = tbase + S::P * k;
+      const T qr = sr[p], qs = ss[p], qt = r_qt[k];
+      T Gqr = G00 * qr;
+      Gqr += G01 * qs;
+      Gqr += G02 * qt;
+      T Gqs = G01 * qr;
+      Gqs += G11 * qs;
+      Gqs += G12 * qt;
+      T Gqt = G02 * qr;
+      Gqt += G12 * qs;
+      Gqt += G22 * qt;
+      sr[p] = lam0 * Gqr;
+      ss[p] = lam0 * Gqs;
+      r_qt[k] = lam0 * Gqt;
+    }
+    // the stage is no longer needed: hand it back to the producer
+    mbar_arrive(&empty[s]);
+    group_sync(1 + g, Nq2);
+
+    // 4. transposed derivatives
+    T r_Aq[Nq];
+#pragma unroll
+    for (int k = 0; k < Nq; ++k) {
+      T v = 0;
+#pragma unroll
+      for (int m = 0; m < Nq; ++m) v += Dm.v[m * Nq + k] * r_qt[m];
+      r_Aq[k] = v;
+    }
+    {
+      T u[Nq];
+#pragma unroll
+      for (int m = 0; m < Nq; ++m) u[m] = sr[S::idx(m, a, b)];
+#pragma unroll
+      for (int ii = 0; ii < Nq; ++ii) {
+        T v = 0;
+#pragma unroll
+        for (int m = 0; m < Nq; ++m) v += Dm.v[m * Nq + ii] * u[m];
+        su[S::idx(ii, a, b)] = v;
+      }
+#pragma unroll
+      for (int m = 0; m < Nq; ++m) u[m] = ss[S::idx(a, m, b)];
+#pragma unroll
+      for (int jj = 0; jj < Nq; ++jj) {
+        T v = 0;
+#pragma unroll
+        for (int m = 0; m < Nq; ++m) v += Dm.v[m * Nq + jj] * u[m];
+        ss[S::idx(a, jj, b)] = v;
+      }
+    }
+    group_sync(1 + g, Nq2);
+
+    // 5. sum and store (coalesced)
+    T* Ae = Aq + (size_t)element * Np + t;
+#pragma unroll
+    for (int k = 0; k < Nq; ++k) {
+      const int p = tbase + S::P * k;
+      T v = r_Aq[k] + su[p] + ss[p];
+      if constexpr (!kPoisson) v += r_mass[k];
+      Ae[k * Nq2] = v;
+    }
+    group_sync(1 + g, Nq2);  // su/ss are rewritten by the next element of this group
+  }
+}
+
+template <typename T, int Nq, int NGROUPS, int NSTAGES, bool kPoisson>
+static int launch_tma(dlong Nelements, const dlong* elementList, const T* ggeo, const T* D_host, const T* lambda0,
+                      const T* lambda1, const T* q, T* Aq, cudaStream_t stream)
+{
+  constexpr int Np = Nq * Nq * Nq;
+  constexpr int NG = kPoisson ? 6 : 7;
+  using S = SlabT<T, Nq>;
+  const size_t smem = ((size_t)NSTAGES * (NG + 1) * Np + (size_t)NGROUPS * 3 * S::size) * sizeof(T) +
+                      2 * NSTAGES * sizeof(uint64_t) + 128;
+  auto kern = ax_tma_kernel<T, Nq, NGROUPS, NSTAGES, kPoisson>;
+  static bool configured = false;
+  if (!configured) {
+    NRSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  DMat<T, Nq> Dm;
+  for (int n = 0; n < Nq * Nq; ++n) Dm.v[n] = D_host[n];
+  int grid = kNumSMs;
+  if (grid > Nelements) grid = Nelements;
+  kern<<<grid, NGROUPS * Nq * Nq + 32, smem, stream>>>(Nelements, elementList, ggeo, Dm, lambda0, lambda1, q, Aq);
+  NRSB_CHECK_LAUNCH();
+  return NRSB_OK;
+}
+
+// variants 4..6 of the axhelm dispatch (Nq = 8, constant coefficients only)
+template <typename T>
+int ax_tma_launch(int Nq, int variant, dlong Nelements, const dlong* elementList, const T* ggeo, const T* D_host,
+                  const T* lambda0, const T* lambda1, int poisson, const T* q, T* Aq, cudaStream_t stream)
+{
+  if (Nelements == 0) return NRSB_OK;
+  if (Nq != 8) {
+    set_last_error("axhelm variants 4-6 (TMA ring) are built for Nq = 8 only");
+    return NRSB_ERR_INVALID;
+  }
+#define NRSB_TMA(G, S_)                                                                                              \
+  return poisson ? launch_tma<T, 8, G, S_, true>(Nelements, elementList, ggeo, D_host, lambda0, lambda1, q, Aq, stream) \
+                 : launch_tma<T, 8, G, S_, false>(Nelements, elementList, ggeo, D_host, lambda0, lambda1, q, Aq, stream);
+  // NSTAGES must be a multiple of NGROUPS: group g then only ever touches stages == g (mod NGROUPS),
+  // i.e. it owns a private sub-ring, and every mbarrier wait is at most one phase behind.
+  if (sizeof(T) == 8) {
+    if (variant == 4) { NRSB_TMA(4, 4) }
+    if (variant == 5) { NRSB_TMA(3, 6) }
+    NRSB_TMA(5, 5)
+  } else {
+    if (variant == 4) { NRSB_TMA(4, 8) }
+    if (variant == 5) { NRSB_TMA(6, 12) }
+    NRSB_TMA(8, 8)
+  }
+#undef NRSB_TMA
+}
+
+template int ax_tma_launch<double>(int, int, dlong, const dlong*, const double*, const double*, const double*,
+                                   const double*, int, const double*, double*, cudaStream_t);
+template int ax_tma_launch<float>(int, int, dlong, const dlong*, const float*, const float*, const float*,
+                                  const float*, int, const float*, float*, cudaStream_t);
+
+}  // namespace nrsb

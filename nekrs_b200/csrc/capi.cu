@@ -22,7 +22,8 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line)
 int ax_default_variant(int Nq, int precision)
 {
   (void)precision;
-  return Nq >= 3 ? 1 : 0;
+  if (Nq == 8) return 5;  // persistent TMA-ring kernel (axhelm_tma.cu)
+  return Nq >= 3 ? 2 : 0;
 }
 
 // process-wide scratch for the kernel-level reductions that return a value to the host

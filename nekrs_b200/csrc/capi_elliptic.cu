@@ -486,7 +486,7 @@ int nrsb_elliptic_autotune(nrsb_elliptic_t h, int* variant_fp64, int* variant_fp
     NRSB_CUDA(cudaMemcpy(e.o_p.p, q.data(), sizeof(double) * m->Nlocal, cudaMemcpyHostToDevice));
     float best = 1e30f;
     int bestV = 0;
-    for (int v = 0; v <= 3; ++v) {
+    for (int v = 0; v <= (m->Nq == 8 ? 6 : 3); ++v) {
       e.ax_variant[0] = v;
       for (int w = 0; w < 2; ++w)
         if ((rc = ellipticAx<double>(&e, m->Nelements, m->o_elementList.p, e.o_p.p, v == 0 ? ref.p : tst.p))) return rc;

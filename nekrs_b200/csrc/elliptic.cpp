@@ -339,6 +339,8 @@ int ellipticSolveSetup(elliptic_t* elliptic)
     if ((rc = elliptic->o_V.alloc(fo * m))) return rc;
     if ((rc = elliptic->o_Z.alloc(fo * (flexible ? m : 1)))) return rc;
     if ((rc = elliptic->o_y.alloc(m))) return rc;
+    if (!flexible)
+      if ((rc = elliptic->o_rtmp.alloc(fo))) return rc;
     elliptic->gmres_H.assign((size_t)(m + 1) * (m + 1), 0.0);
     elliptic->gmres_sn.assign(m, 0.0);
     elliptic->gmres_cs.assign(m, 0.0);
@@ -518,7 +520,10 @@ int pgmres(elliptic_t* elliptic, double* o_r, double* o_x, double tol, int MAXIT
   double* o_Ax = elliptic->o_Ap.p;
   double* o_V = elliptic->o_V.p;
   double* o_Z = elliptic->o_Z.p;
-  double* o_b = elliptic->o_z.p;
+  // The reference aliases b with elliptic->o_z (PGMRES.cpp:128), which the NON-flexible gmresUpdate
+  // overwrites (PGMRES.cpp:83-96), so its restarted non-flexible GMRES computes r = b - Ax from a
+  // clobbered b.  b is kept in its own buffer here when not flexible (deviation noted in DESIGN.md).
+  double* o_b = flexible ? elliptic->o_z.p : elliptic->o_rtmp.p;
   double* S = elliptic->o_scal.p;
   const double* o_weight = elliptic->o_invDegree;
   std::vector<double>&y = elliptic->gmres_y, &H = elliptic->gmres_H, &sn = elliptic->gmres_sn, &cs = elliptic->gmres_cs,

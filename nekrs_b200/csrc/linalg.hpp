@@ -14,6 +14,7 @@ struct DevScalar {
   const double* den = nullptr;
   const double* mul = nullptr;
   double denShift = 0.0;  // value = scale * num * mul / (den + denShift)
+  bool guard = false;     // value = 0 when the denominator is not positive (exactly converged CG)
   static DevScalar host(double v)
   {
     DevScalar s;
@@ -34,7 +35,10 @@ struct DevScalar {
     double v = scale;
     if (num) v *= num[0];
     if (mul) v *= mul[0];
-    if (den) v /= (den[0] + denShift);
+    if (den) {
+      const double d = den[0] + denShift;
+      v = (guard && !(d > 0.0)) ? 0.0 : v / d;
+    }
     return v;
   }
 };

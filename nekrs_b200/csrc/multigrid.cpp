@@ -878,12 +878,16 @@ int coarseSolver_t::solve(float* rhs, float* x)
     if ((rc = axmyz_launch<float>(n, 1.0f, invDiag.p, r.p, z.p, st))) return rc;
     NRSB_CUDA(cudaMemcpyAsync(S + 1, S + 0, sizeof(double), cudaMemcpyDeviceToDevice, st));
     if ((rc = wdot_launch<float>(n, w, r.p, z.p, S + 0, e->ws, st))) return rc;
+    // guarded ratios: a tiny coarse problem converges exactly (p = 0, pAp = 0) before the next
+    // residual check; 0/0 must give 0, not NaN
     DevScalar beta = it ? DevScalar::ratio(S + 0, S + 1) : DevScalar::host(0.0);
+    beta.guard = true;
     if ((rc = axpby_launch<float>(n, DevScalar::host(1.0), z.p, beta, p.p, st))) return rc;
     if ((rc = ellipticOperator<float>(e, p.p, Ap.p))) return rc;
     if ((rc = wdot_launch<float>(n, w, p.p, Ap.p, S + 2, e->ws, st))) return rc;
-    DevScalar alpha = DevScalar::ratio(S + 0, S + 2, 1.0, 1e-300);
-    DevScalar malpha = DevScalar::ratio(S + 0, S + 2, -1.0, 1e-300);
+    DevScalar alpha = DevScalar::ratio(S + 0, S + 2);
+    DevScalar malpha = DevScalar::ratio(S + 0, S + 2, -1.0);
+    alpha.guard = malpha.guard = true;
     if ((rc = axpby_launch<float>(n, alpha, p.p, DevScalar::host(1.0), x, st))) return rc;
     if ((rc = axpby_launch<float>(n, malpha, Ap.p, DevScalar::host(1.0), r.p, st))) return rc;
     if ((it + 1) % checkEvery == 0 || it + 1 == maxIter) {

@@ -515,11 +515,11 @@ class CoarseJPCG:
             o.axmyz(n, 1.0, self.inv_diag, r, z)
             rz_old = rz
             rz = float(np.sum(r.astype(np.float64) * z.astype(np.float64) * wd))
-            beta = rz / rz_old if it else 0.0
+            beta = (rz / rz_old if rz_old > 0.0 else 0.0) if it else 0.0
             o.axpby(n, 1.0, z, beta, p)
             ell.operator(p, Ap)
             pAp = float(np.sum(p.astype(np.float64) * Ap.astype(np.float64) * wd))
-            alpha = rz / (pAp + 1e-300)
+            alpha = rz / pAp if pAp > 0.0 else 0.0
             o.axpby(n, alpha, p, 1.0, x)
             o.axpby(n, -alpha, Ap, 1.0, r)
             if (it + 1) % 8 == 0 or it + 1 == self.max_iter:

@@ -33,7 +33,7 @@ def _gpu():
 # ------------------------------------------------------------------------------------ axhelm
 @pytest.mark.parametrize("N", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11])
 @pytest.mark.parametrize("dt", [np.float64, np.float32])
-@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6])
 def test_axhelm_poisson(orc, N, dt, variant):
     E, Np = 37, (N + 1) ** 3
     r = rng(100 + N)

@@ -1,0 +1,117 @@
+"""Multi-GPU parity check, run under torchrun (one process per GPU):
+
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+        tools/multi_gpu_check.py
+
+Every rank owns a brick of one global kershaw box, sets up the solver with the NVLink halo exchange and
+the device one-shot all-reduce, and compares against the single-rank ORACLE run on the WHOLE mesh
+(restricted to its own elements): fused operator (1e-12), BP5 residual history, BPS5 iteration count.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ["RANK"])
+    world = int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from nekrs_b200 import lib, meshgen, parallel
+    from nekrs_b200.elliptic import Elliptic, pressure_options
+    from nekrs_b200.lib import DeviceBuffer as DB
+    from oracle import driver
+    from oracle.kernels import Orc
+    lib.call("nrsb_set_device", local)
+    comm = parallel.Comm(dist)
+    ok = True
+
+    def report(name, cond, detail=""):
+        nonlocal ok
+        ok &= bool(cond)
+        print("[rank %d] %-34s %s %s" % (rank, name, "OK" if cond else "FAIL", detail), flush=True)
+
+    # ---- scalar all-reduce through peer windows
+    v = comm.allreduce_sum(np.array([rank + 1.0, 10.0 * (rank + 1)]))
+    tot = world * (world + 1) / 2
+    report("one-shot allreduce", np.allclose(v, [tot, 10 * tot]), str(v))
+    for rep in range(50):  # epochs / parity buffers
+        v = comm.allreduce_sum(np.array([float(rep + rank)]))
+        if abs(v[0] - (world * rep + world * (world - 1) / 2)) > 1e-12:
+            report("allreduce epoch %d" % rep, False, str(v))
+            break
+
+    N = int(os.environ.get("CHECK_N", "7"))
+    nel = tuple(int(x) for x in os.environ.get("CHECK_NEL", "4,4,2").split(","))
+    whole = meshgen.box_mesh(N, nel, kershaw_eps=0.3)
+    part = meshgen.box_mesh(N, nel, kershaw_eps=0.3, rank=rank, nranks=world)
+    Np = part.Np
+    # global element index of each local element
+    x0, y0, z0 = part.brick_lo
+    ex, ey, ez = part.brick_n
+    iz, iy, ix = np.meshgrid(np.arange(z0, z0 + ez), np.arange(y0, y0 + ey), np.arange(x0, x0 + ex), indexing="ij")
+    gelem = (ix + nel[0] * (iy + nel[1] * iz)).ravel()
+    gnode = (gelem[:, None] * Np + np.arange(Np)[None, :]).ravel()
+    topo_of = lambda ids: parallel.discover_topology(ids, comm)
+    orc = Orc()
+    nloc = part.Nelements * Np
+
+    # ---- fused operator + BP5
+    opts = {"SOLVER": "PCG", "PRECONDITIONER": "NONE", "MAXIMUM ITERATIONS": "40", "SOLVER TOLERANCE": "1e-15"}
+    ell = Elliptic(part, opts, comm=comm, topo_of=topo_of)
+    ref = driver.OSolver(whole, opts, orc)
+    report("halo rows present", ell.get_int("NhaloGather") > 0, "NhaloGather=%d overlap=%d" % (
+        ell.get_int("NhaloGather"), ell.get_int("overlap")))
+    report("mask ids", np.array_equal(np.sort(gnode[ell.get_array("maskIds", np.int32)]),
+                                      np.intersect1d(ref.ell.mask_ids, gnode)))
+    report("invDegree (global multiplicity)", np.array_equal(ell.get_array("invDegree", np.float64),
+                                                              ref.ell.inv_degree[gnode]))
+    report("volume", abs(ell.get_real("volume") - ref.mesh.volume) < 1e-12)
+    q_glob = np.random.Generator(np.random.PCG64(7)).random(whole.Nelements * Np)
+    out_ref = np.zeros_like(q_glob)
+    ref.ell.operator(q_glob, out_ref)
+    qp = np.zeros(ell.fieldOffset)
+    qp[:nloc] = q_glob[gnode]
+    d_q, d_Aq = DB(like=qp), DB.zeros(ell.fieldOffset, np.float64)
+    for rep in range(3):
+        ell.operator(d_q, d_Aq)
+    err = np.max(np.abs(d_Aq.download()[:nloc] - out_ref[gnode])) / np.max(np.abs(out_ref))
+    report("fused operator (overlap) vs oracle", err < 1e-12, "relerr %.2e" % err)
+    rhs_glob = meshgen.kershaw_rhs(whole)
+    ref.solve(rhs_glob, np.zeros_like(rhs_glob))
+    x = np.zeros(nloc)
+    it = ell.solve_host(np.ascontiguousarray(rhs_glob[gnode]), x)
+    h, hr = ell.res_history(), np.array(ref.res_history)
+    report("BP5 PCG residual history", it == ref.Niter and np.max(np.abs(h - hr) / hr) < 1e-8,
+           "its %d/%d maxrel %.2e" % (it, ref.Niter, np.max(np.abs(h - hr) / hr)))
+
+    # ---- BPS5: p-multigrid preconditioned FGMRES
+    for smoother in ("FOURTHOPTCHEBYSHEV+RAS", "FOURTHOPTCHEBYSHEV+ASM"):
+        opts = pressure_options(**{"MULTIGRID SMOOTHER": smoother})
+        ell2 = Elliptic(part, opts, comm=comm, topo_of=topo_of)
+        ref2 = driver.OSolver(whole, opts, orc)
+        x_ref = ref2.solve(rhs_glob, np.zeros_like(rhs_glob))
+        x = np.zeros(nloc)
+        it = ell2.solve_host(np.ascontiguousarray(rhs_glob[gnode]), x)
+        e = np.max(np.abs(x - x_ref[gnode])) / np.max(np.abs(x_ref))
+        lam = [(ell2.get_real("level%d:maxEig" % k), getattr(ref2.levels[k], "max_eig_value", 0.0)) for k in range(2)]
+        report("BPS5 %s" % smoother, abs(it - ref2.Niter) <= 1 and e < 1e-6,
+               "its %d/%d relerr %.2e maxEig %s" % (it, ref2.Niter, e, lam))
+    dist.barrier()
+    flag = torch.tensor([0 if ok else 1], device="cuda")
+    dist.all_reduce(flag)
+    if rank == 0:
+        print("MULTI_GPU_CHECK", "PASS" if flag.item() == 0 else "FAIL", flush=True)
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() == 0 else 1)
+
+
+if __name__ == "__main__":
+    main()

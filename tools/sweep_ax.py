@@ -55,7 +55,7 @@ def main():
                 d_Aq = DB.zeros(E * Np, dt)
                 d_el = DB(like=np.arange(E, dtype=np.int32))
                 lam = DB(like=np.ones(1, dtype=dt))
-                for variant in (0, 1, 2, 3):
+                for variant in (0, 1, 2, 3, 4, 5, 6):
                     fn = lambda: ops.ellipticPartialAxCoeffHex3D(N, d_el, d_g, D, d_q, d_Aq, Nelements=E,
                                                                  lambda0=lam, variant=variant, dtype=dt)
                     med, mn = time_fn(fn)
