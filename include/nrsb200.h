@@ -58,6 +58,9 @@ int nrsb_event_destroy(void* event);
 int nrsb_event_record(void* event, void* stream);
 int nrsb_event_synchronize(void* event);
 int nrsb_event_elapsed_ms(void* start, void* stop, float* ms);
+/* cudaProfilerStart/Stop, for `ncu --profile-from-start off` */
+int nrsb_profiler_start(void);
+int nrsb_profiler_stop(void);
 int nrsb_stream_create(void** stream);
 int nrsb_stream_destroy(void* stream);
 

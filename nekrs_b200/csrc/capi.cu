@@ -1,4 +1,6 @@
 // capi.cu -- extern "C" surface declared in include/nrsb200.h (kernel-level + plumbing + ogs).
+#include <cuda_profiler_api.h>
+
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -175,6 +177,16 @@ int nrsb_event_synchronize(void* event)
 int nrsb_event_elapsed_ms(void* start, void* stop, float* ms)
 {
   NRSB_CUDA(cudaEventElapsedTime(ms, (cudaEvent_t)start, (cudaEvent_t)stop));
+  return NRSB_OK;
+}
+int nrsb_profiler_start(void)
+{
+  NRSB_CUDA(cudaProfilerStart());
+  return NRSB_OK;
+}
+int nrsb_profiler_stop(void)
+{
+  NRSB_CUDA(cudaProfilerStop());
   return NRSB_OK;
 }
 int nrsb_stream_create(void** stream)

@@ -233,13 +233,19 @@ class MGSolver_t {
 class coarseSolver_t {
  public:
   pMGLevel* level = nullptr;
-  dbuf<float> r, z, p, Ap, w, invDiag;
+  int NT = 0;  // unique unmasked coarse nodes on this rank (T-vector)
+  bool multiRank = false;
+  dbuf<int> d_rowStarts, d_cols, d_rowNode, d_tIndex;
+  dbuf<float> d_vals, d_weight, invDiag, x, r, u, p, s, w;
   dbuf<double> scal;
+  std::unique_ptr<ogs_t> ogsT;
+  std::unique_ptr<oogs_t> oogsT;
   int maxIter = 200;
   double tol = 1e-3;
   int lastIter = 0;
   int setup(pMGLevel* lvl, int maxIter, double tol);
   int solve(float* rhs, float* x);
+  int spmv_dots(bool first);
 };
 
 class precon_t {

@@ -14,10 +14,9 @@
 // (NVLink stores + flag, comm.cu) and leaves the scalar on the device.  The result is
 // deterministic for a given (N, grid) and bit-identical on every rank.
 #include "linalg.hpp"
+#include "reduce.cuh"
 
 namespace nrsb {
-
-constexpr int kRedThreads = 256;
 
 static inline int stream_grid(long N, int perThread = 4)
 {
@@ -183,111 +182,7 @@ NRSB_INST(float)
 #undef NRSB_INST
 
 // ----------------------------------------------------------------------------- reductions
-__device__ __forceinline__ double block_sum(double v, double* s_red)
-{
-  // s_red: kRedThreads/32 doubles.  Result valid in thread 0.
-  v = warp_sum(v);
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  __syncthreads();
-  if (lane == 0) s_red[wid] = v;
-  __syncthreads();
-  if (wid == 0) {
-    v = (lane < kRedThreads / 32) ? s_red[lane] : 0.0;
-    v = warp_sum(v);
-  }
-  return v;
-}
-
-// cross-rank one-shot all-reduce executed by thread 0 of the last block (see comm.cu)
-__device__ void peer_allreduce(const PeerReduce& P, double* vals, int nv);
-
-template <int NV, typename Op>
-__global__ void __launch_bounds__(kRedThreads) reduce_kernel(long N, Op op, int nv, double* out, ReduceWs ws)
-{
-  __shared__ double s_red[kRedThreads / 32];
-  __shared__ bool s_last;
-  double acc[NV];
-#pragma unroll
-  for (int v = 0; v < NV; ++v) acc[v] = 0.0;
-  const long stride = (long)gridDim.x * blockDim.x;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) op(i, acc);
-
-#pragma unroll
-  for (int v = 0; v < NV; ++v) {
-    const double b = block_sum(acc[v], s_red);
-    if (threadIdx.x == 0 && v < nv) ws.partials[(size_t)blockIdx.x * kMaxRed + v] = b;
-  }
-  if (threadIdx.x == 0) {
-    __threadfence();
-    const unsigned t = atomicAdd(ws.ticket, 1u);
-    s_last = (t == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  double tot[NV];
-#pragma unroll
-  for (int v = 0; v < NV; ++v) {
-    double a = 0.0;
-    if (v < nv)
-      for (int b = threadIdx.x; b < (int)gridDim.x; b += kRedThreads)
-        a += __ldcg(&ws.partials[(size_t)b * kMaxRed + v]);
-    tot[v] = block_sum(a, s_red);
-  }
-  if (threadIdx.x == 0) {
-    if (ws.peer.nranks > 1) peer_allreduce(ws.peer, tot, nv);
-#pragma unroll
-    for (int v = 0; v < NV; ++v)
-      if (v < nv) out[v] = tot[v];
-    *ws.ticket = 0u;
-  }
-}
-
-__device__ void peer_allreduce(const PeerReduce& P, double* vals, int nv)
-{
-  // epoch e, parity-double-buffered slots: slots[p] = peer p's window [2][nranks][kMaxRed]
-  const unsigned long long e = *P.epoch + 1ull;
-  *P.epoch = e;
-  const int par = (int)(e & 1ull);
-  for (int p = 0; p < P.nranks; ++p) {
-    double* dst = P.slots[p] + ((size_t)par * P.nranks + P.rank) * kMaxRed;
-    for (int v = 0; v < nv; ++v) dst[v] = vals[v];
-  }
-  __threadfence_system();
-  for (int p = 0; p < P.nranks; ++p) {
-    volatile unsigned long long* f = P.flags[p] + P.rank;
-    *f = e;
-  }
-  volatile unsigned long long* mine = P.flags[P.rank];
-  const volatile double* loc = P.slots[P.rank] + (size_t)par * P.nranks * kMaxRed;
-  for (int v = 0; v < nv; ++v) vals[v] = 0.0;
-  for (int p = 0; p < P.nranks; ++p) {
-    while (mine[p] < e) {
-    }
-    __threadfence_system();
-    for (int v = 0; v < nv; ++v) vals[v] += loc[(size_t)p * kMaxRed + v];
-  }
-}
-
-static inline int red_grid(long N)
-{
-  long b = (N + (long)kRedThreads * 8 - 1) / ((long)kRedThreads * 8);
-  if (b > kMaxRedBlocks) b = kMaxRedBlocks;
-  if (b < 1) b = 1;
-  return (int)b;
-}
-
-template <int NV, typename Op>
-static int reduce_launch(long N, Op op, int nv, double* out, const ReduceWs& ws, cudaStream_t s)
-{
-  if (!ws.partials || !ws.ticket) {
-    set_last_error("reduction workspace not initialised");
-    return NRSB_ERR_INVALID;
-  }
-  reduce_kernel<NV, Op><<<red_grid(N), kRedThreads, 0, s>>>(N, op, nv, out, ws);
-  NRSB_CHECK_LAUNCH();
-  return NRSB_OK;
-}
+// (template in reduce.cuh)
 
 template <typename T>
 int wdot_launch(long N, const T* w, const T* x, const T* y, double* out, const ReduceWs& ws, cudaStream_t s)

@@ -837,76 +837,6 @@ int MGSolver_t::runVcycle(int k)
 }
 
 // ------------------------------------------------------------------------------------------
-// coarse solver stand-in: Jacobi-PCG on the assembled N=1 operator, fp32 vectors, fp64 scalars kept
-// on the device; the only host round trip is one residual norm every `checkEvery` iterations.
-// ------------------------------------------------------------------------------------------
-int coarseSolver_t::setup(pMGLevel* lvl, int maxIter_, double tol_)
-{
-  level = lvl;
-  maxIter = maxIter_;
-  tol = tol_;
-  const long n = lvl->Nrows;
-  int rc;
-  if ((rc = r.alloc(n))) return rc;
-  if ((rc = z.alloc(n))) return rc;
-  if ((rc = p.alloc(n))) return rc;
-  if ((rc = Ap.alloc(n))) return rc;
-  if ((rc = invDiag.alloc(n))) return rc;
-  if ((rc = scal.alloc(16))) return rc;
-  return ellipticBuildDiagonal<float>(lvl->elliptic, invDiag.p);
-}
-
-int coarseSolver_t::solve(float* rhs, float* x)
-{
-  // coarseLevel_t::solve (coarseLevel.cpp:182-222) gathers E->T with the weight, solves, scatters T->E.
-  // Working on the E-vector with the gather-scattered operator is the same linear system: the rhs
-  // entering here is already gather-scattered (pMGLevel::coarsen), so b_T = gather(weight * rhs) and
-  // x_E = scatter(x_T) are what PCG with weighted inner products computes.
-  elliptic_t* e = level->elliptic;
-  cudaStream_t st = e->stream;
-  const long n = level->Nrows;
-  const float* w = e->o_invDegreePfloat;
-  double* S = scal.p;  // 0 rz, 1 rz_old, 2 pAp, 3 rr, 4 rr0
-  int rc;
-  if ((rc = fill_launch<float>(n, 0.f, x, st))) return rc;
-  NRSB_CUDA(cudaMemcpyAsync(r.p, rhs, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
-  if ((rc = wnorm2_launch<float>(n, w, r.p, S + 4, e->ws, st))) return rc;
-  int it = 0;
-  const int checkEvery = 8;
-  double h[2];
-  for (it = 0; it < maxIter; ++it) {
-    if ((rc = axmyz_launch<float>(n, 1.0f, invDiag.p, r.p, z.p, st))) return rc;
-    NRSB_CUDA(cudaMemcpyAsync(S + 1, S + 0, sizeof(double), cudaMemcpyDeviceToDevice, st));
-    if ((rc = wdot_launch<float>(n, w, r.p, z.p, S + 0, e->ws, st))) return rc;
-    // guarded ratios: a tiny coarse problem converges exactly (p = 0, pAp = 0) before the next
-    // residual check; 0/0 must give 0, not NaN
-    DevScalar beta = it ? DevScalar::ratio(S + 0, S + 1) : DevScalar::host(0.0);
-    beta.guard = true;
-    if ((rc = axpby_launch<float>(n, DevScalar::host(1.0), z.p, beta, p.p, st))) return rc;
-    if ((rc = ellipticOperator<float>(e, p.p, Ap.p))) return rc;
-    if ((rc = wdot_launch<float>(n, w, p.p, Ap.p, S + 2, e->ws, st))) return rc;
-    DevScalar alpha = DevScalar::ratio(S + 0, S + 2);
-    DevScalar malpha = DevScalar::ratio(S + 0, S + 2, -1.0);
-    alpha.guard = malpha.guard = true;
-    if ((rc = axpby_launch<float>(n, alpha, p.p, DevScalar::host(1.0), x, st))) return rc;
-    if ((rc = axpby_launch<float>(n, malpha, Ap.p, DevScalar::host(1.0), r.p, st))) return rc;
-    if ((it + 1) % checkEvery == 0 || it + 1 == maxIter) {
-      if ((rc = wnorm2_launch<float>(n, w, r.p, S + 3, e->ws, st))) return rc;
-      NRSB_CUDA(cudaMemcpyAsync(e->h_scal + 32, S + 3, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
-      NRSB_CUDA(cudaStreamSynchronize(st));
-      h[0] = e->h_scal[32];
-      h[1] = e->h_scal[33];
-      if (!(h[0] > tol * tol * h[1])) {
-        ++it;
-        break;
-      }
-    }
-  }
-  lastIter = it;
-  return NRSB_OK;
-}
-
-// ------------------------------------------------------------------------------------------
 // level construction (ellipticMultiGridSetup.cpp, ellipticBuildMultigridLevel*.cpp, createMeshMG)
 // ------------------------------------------------------------------------------------------
 static int build_level_elliptic(elliptic_t* base, mesh_t* baseMesh, int Nc, std::unique_ptr<mesh_t>& meshOut,

@@ -494,40 +494,79 @@ class OLevel:
 
 
 class CoarseJPCG:
-    """Coarse-solve stand-in shared with the product (multigrid.cpp coarseSolver_t)."""
+    """Coarse-solve stand-in shared with the product (coarse.cu coarseSolver_t): Jacobi-PCG in the
+    Chronopoulos-Gear form on the ASSEMBLED N=1 operator (the matrix of ellipticBuildFEMHex3D,
+    MG/ellipticBuildFEM.cpp:73-305), unknowns = unique unmasked nodes.
+
+    The element matrices are obtained here by applying the oracle's matrix-free N=1 operator to the
+    eight unit vectors (an independent route to the same matrix the product assembles from the
+    closed-form entries)."""
 
     def __init__(self, orc, lvl: OLevel, max_iter, tol):
+        import scipy.sparse as sp
         self.orc, self.lvl, self.max_iter, self.tol = orc, lvl, max_iter, tol
-        self.inv_diag = lvl.ell.build_inv_diag(f32)
+        ell, m = lvl.ell, lvl.ell.mesh
+        E, Np = m.E, m.Np
+        ogs = ell.ogs
+        NT = ogs.Ngather
+        t_index = np.full(m.Nlocal, -1, dtype=np.int64)
+        counts = np.diff(ogs.offsets)
+        t_index[ogs.gather_ids] = np.repeat(np.arange(NT), counts)
+        self.row_node = ogs.gather_ids[ogs.offsets[:-1]]
+        self.t_index = t_index
+        Ae = np.zeros((E, Np, Np))
+        for mm in range(Np):
+            q = np.zeros((E, Np))
+            q[:, mm] = 1.0
+            out = np.zeros(E * Np)
+            orc.ax(m.N, m.element_list, m.ggeo, m.D, np.ascontiguousarray(q.reshape(-1)), out)
+            Ae[:, :, mm] = out.reshape(E, Np)
+        tn = t_index.reshape(E, Np)
+        rows = np.repeat(tn[:, :, None], Np, axis=2).reshape(-1)
+        cols = np.repeat(tn[:, None, :], Np, axis=1).reshape(-1)
+        keep = (rows >= 0) & (cols >= 0)
+        A = sp.coo_matrix((Ae.reshape(-1)[keep], (rows[keep], cols[keep])), shape=(NT, NT)).tocsr()
+        A.sum_duplicates()
+        self.A = A.astype(f32)
+        self.inv_diag = (f32(1.0) / self.A.diagonal()).astype(f32)
+        self.NT = NT
         self.last_iter = 0
 
-    def solve(self, rhs, x):
-        o, ell, n = self.orc, self.lvl.ell, self.lvl.Nrows
-        w = ell.inv_degree_f
-        x[:] = 0
-        r = rhs.copy()
-        z, p, Ap = np.zeros(n, f32), np.zeros(n, f32), np.zeros(n, f32)
-        wd, rd = w.astype(np.float64), None
-        rr0 = float(np.sum(r.astype(np.float64) ** 2 * wd))
-        rz = 0.0
+    def spmv_dots(self, r, u):
+        w = (self.A @ u).astype(f32)
+        ud = u.astype(np.float64)
+        return w, float(np.sum(r.astype(np.float64) * ud)), float(np.sum(w.astype(np.float64) * ud))
+
+    def solve(self, rhs, xE):
+        b = rhs[self.row_node].astype(f32)
+        x = np.zeros(self.NT, f32)
+        r = b.copy()
+        u = (self.inv_diag * r).astype(f32)
+        p, s = np.zeros(self.NT, f32), np.zeros(self.NT, f32)
+        w, gamma, delta = self.spmv_dots(r, u)
+        gamma0 = gamma
+        beta = 0.0
+        alpha = gamma / delta if delta > 0.0 else 0.0
         it = 0
-        for it in range(self.max_iter):
-            o.axmyz(n, 1.0, self.inv_diag, r, z)
-            rz_old = rz
-            rz = float(np.sum(r.astype(np.float64) * z.astype(np.float64) * wd))
-            beta = (rz / rz_old if rz_old > 0.0 else 0.0) if it else 0.0
-            o.axpby(n, 1.0, z, beta, p)
-            ell.operator(p, Ap)
-            pAp = float(np.sum(p.astype(np.float64) * Ap.astype(np.float64) * wd))
-            alpha = rz / pAp if pAp > 0.0 else 0.0
-            o.axpby(n, alpha, p, 1.0, x)
-            o.axpby(n, -alpha, Ap, 1.0, r)
-            if (it + 1) % 8 == 0 or it + 1 == self.max_iter:
-                rr = float(np.sum(r.astype(np.float64) ** 2 * wd))
-                if not (rr > self.tol * self.tol * rr0):
-                    it += 1
+        for it in range(1, self.max_iter + 1):
+            a32, b32 = f32(alpha), f32(beta)
+            p = (u + b32 * p).astype(f32)
+            s = (w + b32 * s).astype(f32)
+            x = (x + a32 * p).astype(f32)
+            r = (r - a32 * s).astype(f32)
+            u = (self.inv_diag * r).astype(f32)
+            w, gn, delta = self.spmv_dots(r, u)
+            beta = gn / gamma if gamma > 0.0 else 0.0
+            den = delta - beta * gn / alpha if alpha != 0.0 else delta
+            alpha = gn / den if den > 0.0 else 0.0
+            gamma = gn
+            if it % 8 == 0 or it == self.max_iter:
+                if not (gamma > self.tol * self.tol * gamma0):
                     break
-        self.last_iter = it
+        self.last_iter = min(it, self.max_iter)
+        xE[:] = 0
+        sel = self.t_index >= 0
+        xE[sel] = x[self.t_index[sel]]
 
 
 # ------------------------------------------------------------------------------------------ solver

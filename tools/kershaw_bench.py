@@ -71,10 +71,15 @@ def main():
                 lib.call("nrsb_memcpy_d2d", lib.vp(d_r), lib.vp(d_r0), fo * 8, None)
                 lib.call("nrsb_memset", lib.vp(d_x), 0, fo * 8, None)
                 barrier()
+                prof = timed and os.environ.get("NRSB_PROFILE") == "1"
+                if prof:
+                    lib.call("nrsb_profiler_start")
                 t = time.perf_counter()
                 ell.solve(d_r, d_x)
                 lib.synchronize()
                 dt = time.perf_counter() - t
+                if prof:
+                    lib.call("nrsb_profiler_stop")
                 if timed:
                     times.append(dt)
         if dist is not None:
