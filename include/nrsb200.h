@@ -126,6 +126,13 @@ int nrsb_preFDM(int Nq, nrsb_dlong Nelements, const float* d_u, float* d_work1, 
 int nrsb_fusedFDM(int Nq, int restrict_, nrsb_dlong Nelements, const nrsb_dlong* d_elementList, float* d_Su,
                   const float* d_Sx, const float* d_Sy, const float* d_Sz, const float* d_invL, const float* d_wts,
                   float* d_u, void* stream);
+/* fusedFDM kernel variant (the reference autotunes fusedFDM_v0..v4, benchmarkFDM.cpp:38-296):
+ * 0 = one pencil per thread, 1 = register-blocked pencil pairs (default, even extended sizes) */
+int nrsb_set_fdm_variant(int variant);
+/* coarse-grid solve variant (stands where coarseLevel_t::solve calls BoomerAMG, MG/coarseLevel.cpp:182-222):
+ * 1 = whole PCG solve in one thread-block-cluster kernel when the coarse grid fits (default, one rank),
+ * 0 = two launches per iteration (the path for several ranks) */
+int nrsb_set_coarse_variant(int variant);
 int nrsb_postFDM(int Nq, nrsb_dlong Nelements, float* d_work1, float* d_work2, float* d_Su, const float* d_wts,
                  void* stream);
 

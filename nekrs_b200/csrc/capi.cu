@@ -7,6 +7,7 @@
 
 #include "gs.hpp"
 #include "kernels.hpp"
+#include "host.hpp"
 #include "linalg.hpp"
 
 namespace nrsb {
@@ -405,6 +406,16 @@ int nrsb_fusedFDM(int Nq, int restrict_, nrsb_dlong Nelements, const nrsb_dlong*
   NRSB_REQUIRE(!restrict_ || d_wts, "RAS (restrict=1) needs wts");
   return fused_fdm_launch(Nq, restrict_, Nelements, d_elementList, d_Su, d_Sx, d_Sy, d_Sz, d_invL, d_wts, d_u,
                           ST(stream));
+}
+int nrsb_set_coarse_variant(int variant)
+{
+  coarseSolver_t::variant = variant;
+  return NRSB_OK;
+}
+int nrsb_set_fdm_variant(int variant)
+{
+  set_fdm_variant(variant);
+  return NRSB_OK;
 }
 int nrsb_postFDM(int Nq, nrsb_dlong Nelements, float* d_work1, float* d_work2, float* d_Su, const float* d_wts,
                  void* stream)

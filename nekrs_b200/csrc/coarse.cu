@@ -83,15 +83,28 @@ __global__ void __launch_bounds__(kBlockSize)
   u[t] = invDiag[t] * rn;
 }
 
+__device__ __forceinline__ float ell_row(int NT, int W, const int* __restrict__ cols, const float* __restrict__ vals,
+                                         const float* __restrict__ u, long t)
+{
+  float acc = 0.f;
+  for (int k = 0; k < W; k += 3) {  // W is a multiple of 3; summation order = ascending column, as CSR
+    const int c0 = cols[(size_t)k * NT + t], c1 = cols[(size_t)(k + 1) * NT + t], c2 = cols[(size_t)(k + 2) * NT + t];
+    const float v0 = vals[(size_t)k * NT + t], v1 = vals[(size_t)(k + 1) * NT + t], v2 = vals[(size_t)(k + 2) * NT + t];
+    const float u0 = u[c0], u1 = u[c1], u2 = u[c2];
+    acc += v0 * u0;
+    acc += v1 * u1;
+    acc += v2 * u2;
+  }
+  return acc;
+}
+
 __global__ void __launch_bounds__(kBlockSize)
-    coarse_spmv_kernel(int NT, const int* __restrict__ rowStarts, const int* __restrict__ cols,
-                       const float* __restrict__ vals, const float* __restrict__ u, float* __restrict__ w)
+    coarse_spmv_kernel(int NT, int W, const int* __restrict__ cols, const float* __restrict__ vals,
+                       const float* __restrict__ u, float* __restrict__ w)
 {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= NT) return;
-  float acc = 0.f;
-  for (int c = rowStarts[t]; c < rowStarts[t + 1]; ++c) acc += vals[c] * u[cols[c]];
-  w[t] = acc;
+  w[t] = ell_row(NT, W, cols, vals, u, t);
 }
 
 __global__ void __launch_bounds__(kBlockSize)
@@ -182,17 +195,23 @@ int coarseSolver_t::setup(pMGLevel* lvl, int maxIter_, double tol_)
                 rows[tn][tm] += lambda0 * val + lambda1 * valDiag;
               }
         }
-  std::vector<int> rowStarts(NT + 1, 0), cols;
-  std::vector<float> vals, diag(NT, 0.f);
+  // ELL storage, column-major (entry k of row t at [k*NT + t]): fixed trip count -> the loads of one
+  // row are independent and coalesced across rows.  Padding: column = own row, value = 0.
+  ellWidth = 0;
+  for (int t = 0; t < NT; ++t) ellWidth = std::max(ellWidth, (int)rows[t].size());
+  ellWidth = (ellWidth + 2) / 3 * 3;
+  std::vector<int> cols((size_t)ellWidth * NT);
+  std::vector<float> vals((size_t)ellWidth * NT, 0.f), diag(NT, 0.f);
   for (int t = 0; t < NT; ++t) {
+    int k = 0;
     for (auto& kv : rows[t]) {
-      cols.push_back(kv.first);
-      vals.push_back((float)kv.second);
+      cols[(size_t)k * NT + t] = kv.first;
+      vals[(size_t)k * NT + t] = (float)kv.second;
       if (kv.first == t) diag[t] = (float)kv.second;
+      ++k;
     }
-    rowStarts[t + 1] = (int)cols.size();
+    for (; k < ellWidth; ++k) cols[(size_t)k * NT + t] = t;
   }
-  if ((rc = d_rowStarts.upload(rowStarts))) return rc;
   if ((rc = d_cols.upload(cols))) return rc;
   if ((rc = d_vals.upload(vals))) return rc;
   if ((rc = d_rowNode.upload(rowNode))) return rc;
@@ -227,8 +246,10 @@ int coarseSolver_t::setup(pMGLevel* lvl, int maxIter_, double tol_)
   if ((rc = s.alloc(NT))) return rc;
   if ((rc = w.alloc(NT))) return rc;
   if ((rc = scal.alloc(C_COUNT))) return rc;
-  return NRSB_OK;
+  return plan_cluster();
 }
+
+int coarseSolver_t::variant = 1;
 
 // w = A u ; gamma = (r,u) ; delta = (w,u) ; alpha, beta updated by the last block
 int coarseSolver_t::spmv_dots(bool first)
@@ -236,16 +257,15 @@ int coarseSolver_t::spmv_dots(bool first)
   elliptic_t* e = level->elliptic;
   cudaStream_t st = e->stream;
   double* S = scal.p;
-  const int* rs = d_rowStarts.p;
   const int* cl = d_cols.p;
+  const int W = ellWidth, nt = NT;
   const float* vl = d_vals.p;
   const float *up = u.p, *rp = r.p, *wt = d_weight.p;
   float* wp = w.p;
   CgPost post{S, first ? 1 : 0};
   if (!multiRank) {
     auto op = [=] __device__(long t, double* acc) {
-      float a = 0.f;
-      for (int c = rs[t]; c < rs[t + 1]; ++c) a += vl[c] * up[cl[c]];
+      const float a = ell_row(nt, W, cl, vl, up, t);
       wp[t] = a;
       const double ut = (double)up[t], wgt = (double)wt[t];
       acc[0] += (double)rp[t] * ut * wgt;
@@ -253,7 +273,7 @@ int coarseSolver_t::spmv_dots(bool first)
     };
     return reduce_launch<2>(NT, op, 2, S + C_TMP0, e->ws, st, post, 1);
   }
-  coarse_spmv_kernel<<<(NT + kBlockSize - 1) / kBlockSize, kBlockSize, 0, st>>>(NT, rs, cl, vl, up, wp);
+  coarse_spmv_kernel<<<(NT + kBlockSize - 1) / kBlockSize, kBlockSize, 0, st>>>(NT, W, cl, vl, up, wp);
   NRSB_CHECK_LAUNCH();
   int rc = oogsT->startFinish<float>(wp, 1, 0, gs_op::add, 0, nullptr, st);
   if (rc) return rc;
@@ -272,13 +292,14 @@ int coarseSolver_t::solve(float* rhs, float* xE)
   const int grid = (NT + kBlockSize - 1) / kBlockSize;
   double* S = scal.p;
   int rc;
+  if (variant == 1 && clusterSize > 0) return solve_cluster(rhs, xE);
+  iterOnDevice = false;
   lastIter = 0;
   if (NT > 0) {
     coarse_init_kernel<<<grid, kBlockSize, 0, st>>>(NT, d_rowNode.p, rhs, invDiag.p, x.p, r.p, u.p, p.p, s.p);
     NRSB_CHECK_LAUNCH();
   }
   if ((rc = spmv_dots(true))) return rc;
-  const int checkEvery = 8;
   int it = 0;
   for (it = 1; it <= maxIter; ++it) {
     if (NT > 0) {

@@ -259,11 +259,22 @@ static int fused_launch(int restrict_, dlong Nelements, const dlong* elementList
       return NRSB_ERR_INVALID;                                      \
   }
 
+int fused_fdm_v1_launch(int Nq, int restrict_, dlong Nelements, const dlong* elementList, float* Su, const float* Sx,
+                        const float* Sy, const float* Sz, const float* invL, const float* wts, float* u,
+                        cudaStream_t stream, int epb);
+static int g_fdm_variant = 1;  // 0: one pencil per thread (this file); 1: register-blocked pairs (fdm_v1.cu)
+void set_fdm_variant(int v) { g_fdm_variant = v; }
+
 int fused_fdm_launch(int Nq, int restrict_, dlong Nelements, const dlong* elementList, float* Su, const float* Sx,
                      const float* Sy, const float* Sz, const float* invL, const float* wts, float* u,
                      cudaStream_t stream)
 {
   if (Nelements == 0) return NRSB_OK;
+  if (g_fdm_variant >= 1) {
+    const int rc = fused_fdm_v1_launch(Nq, restrict_, Nelements, elementList, Su, Sx, Sy, Sz, invL, wts, u, stream,
+                                       g_fdm_variant >= 10 ? g_fdm_variant - 10 : 0);
+    if (rc != 1) return rc;  // 1 = size not covered (odd extended size): fall through to variant 0
+  }
 #define CALL(n) return fused_launch<n>(restrict_, Nelements, elementList, Su, Sx, Sy, Sz, invL, wts, u, stream);
   NRSB_FDM_SWITCH(CALL)
 #undef CALL

@@ -234,6 +234,7 @@ class coarseSolver_t {
  public:
   pMGLevel* level = nullptr;
   int NT = 0;  // unique unmasked coarse nodes on this rank (T-vector)
+  int ellWidth = 0;
   bool multiRank = false;
   dbuf<int> d_rowStarts, d_cols, d_rowNode, d_tIndex;
   dbuf<float> d_vals, d_weight, invDiag, x, r, u, p, s, w;
@@ -242,10 +243,19 @@ class coarseSolver_t {
   std::unique_ptr<oogs_t> oogsT;
   int maxIter = 200;
   double tol = 1e-3;
+  int checkEvery = 8;  // convergence is tested every checkEvery iterations (both solve paths)
   int lastIter = 0;
+  bool iterOnDevice = false;
+  // single-kernel cluster path (coarse_cluster.cu); clusterSize == 0 -> multi-launch path
+  int clusterSize = 0, clusterRPC = 0, clusterRmax = 0, clusterMatInSmem = 0;
+  size_t clusterSmem = 0;
+  static int variant;  // 1 (default): cluster kernel when it fits; 0: always the multi-launch path
   int setup(pMGLevel* lvl, int maxIter, double tol);
   int solve(float* rhs, float* x);
   int spmv_dots(bool first);
+  int plan_cluster();
+  int solve_cluster(float* rhs, float* x);
+  int iterations();
 };
 
 class precon_t {

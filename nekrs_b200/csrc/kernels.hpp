@@ -15,6 +15,7 @@ int ax_default_variant(int Nq, int precision);
 int fused_fdm_launch(int Nq, int restrict_, dlong Nelements, const dlong* elementList, float* Su, const float* Sx,
                      const float* Sy, const float* Sz, const float* invL, const float* wts, float* u,
                      cudaStream_t stream);
+void set_fdm_variant(int v);
 int pre_fdm_launch(int Nq, dlong Nelements, const float* u, float* work1, cudaStream_t stream);
 int post_fdm_launch(int Nq, dlong Nelements, const float* work1, const float* work2, float* Su, const float* wts,
                     cudaStream_t stream);

@@ -244,3 +244,32 @@ def test_error_codes():
     n = ell.fieldOffset
     with pytest.raises(lib.NrsbError):
         ell.solve(DB.zeros(n, np.float64), DB.zeros(n, np.float64))
+
+
+@pytest.mark.parametrize("nel", [(3, 3, 3), (6, 5, 4)])
+def test_coarse_cluster_kernel_matches_multilaunch_and_oracle(orc, nel):
+    """The single-kernel cluster PCG (coarse_cluster.cu) and the two-launches-per-iteration path run the
+    same recurrences: same iteration count, same solution to fp32 round-off; both follow the oracle."""
+    import ctypes
+    from nekrs_b200 import lib as _lib
+    mesh, opts, ell, ref = _mg_case(orc, 3, nel, "FOURTHOPTCHEBYSHEV+RAS")
+    k = ell.get_int("nLevels") - 1
+    n1 = ell.get_int("level%d:Nlocal" % k)
+    rhs = np.random.Generator(np.random.PCG64(3)).random(n1).astype(np.float32) - 0.5
+    Lc = ref.levels[k]
+    rhs[Lc.ell.mask_ids] = 0
+    out = {}
+    try:
+        for variant in (1, 0):
+            _lib.call("nrsb_set_coarse_variant", ctypes.c_int(variant))
+            d_x = DB.zeros(n1, np.float32)
+            ell.level_op(k, "coarseSolve", DB(like=rhs), d_x)
+            out[variant] = (d_x.download(), ell.get_int("coarseIterations"))
+    finally:
+        _lib.call("nrsb_set_coarse_variant", ctypes.c_int(1))
+    assert out[1][1] == out[0][1] and out[1][1] > 0
+    assert relerr(out[1][0], out[0][0]) < 2e-5
+    x_ref = np.zeros(n1, np.float32)
+    ref.coarse.solve(rhs, x_ref)
+    assert abs(out[1][1] - ref.coarse.last_iter) <= 8
+    assert relerr(out[1][0], x_ref) < 2e-3

@@ -271,7 +271,10 @@ def test_chebyshev_updates(orc):
 # ------------------------------------------------------------------------------------ FDM / transfers
 @pytest.mark.parametrize("N", [1, 2, 3, 5, 7, 9])
 @pytest.mark.parametrize("restrict", [1, 0])
-def test_fdm(orc, N, restrict):
+@pytest.mark.parametrize("fdm_variant", [0, 1])
+def test_fdm(orc, N, restrict, fdm_variant):
+    import ctypes
+    lib.call("nrsb_set_fdm_variant", ctypes.c_int(fdm_variant))
     E = 23
     Nq, Nqe = N + 1, N + 3
     r = rng(20 + N)
