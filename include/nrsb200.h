@@ -51,7 +51,7 @@ int nrsb_memcpy_d2d(void* d_dst, const void* d_src, size_t bytes, void* stream);
 int nrsb_memset(void* d_dst, int value, size_t bytes, void* stream);
 int nrsb_stream_synchronize(void* stream);
 int nrsb_device_synchronize(void);
-int nrsb_l2_flush(void* stream); /* writes a >L2-sized scratch buffer (benchmark hygiene) */
+int nrsb_l2_flush(void* stream); /* writes, then reads back, a 2xL2 scratch buffer: cold AND clean L2 (benchmark hygiene) */
 /* CUDA events for device-side timing on the launching stream (timer::tic/toc, timer.cpp:199-233) */
 int nrsb_event_create(void** event);
 int nrsb_event_destroy(void* event);

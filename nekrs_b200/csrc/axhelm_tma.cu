@@ -51,6 +51,22 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// geometric factors are read exactly once per operator application: mark them evict-first so that the
+// 117 MB stream does not push the E-vectors (q, Aq: what the gather-scatter touches next) out of L2
+__device__ __forceinline__ uint64_t l2_evict_first_policy()
+{
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t pol)
+{
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+      : "memory");
+}
 __device__ __forceinline__ void group_sync(int id, int nthreads)
 {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -114,13 +130,14 @@ __global__ void __launch_bounds__(NGROUPS* Nq* Nq + 32, 1)
   if (tid >= nConsumers) {
     // ===== producer warp: one lane streams element slabs into the ring =====
     if (tid == nConsumers) {
+      const uint64_t pol = l2_evict_first_policy();
       for (int i = 0; i < myCount; ++i) {
         const int s = i % NSTAGES;
         if (i >= NSTAGES) mbar_wait(&empty[s], ((i / NSTAGES) - 1) & 1);
         const dlong element = elementList[blockIdx.x + (dlong)i * gridDim.x];
         T* st = stages + (size_t)s * stageElems;
         mbar_expect_tx(&full[s], gBytes + qBytes);
-        bulk_g2s(st, ggeo + (size_t)element * 7 * Np, gBytes, &full[s]);
+        bulk_g2s_hint(st, ggeo + (size_t)element * 7 * Np, gBytes, &full[s], pol);
         bulk_g2s(st + NG * Np, q + (size_t)element * Np, qBytes, &full[s]);
       }
     }

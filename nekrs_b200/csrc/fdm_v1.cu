@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(FdmV1<Nqe>::TPE* EPB)
   for (int q = 0; q < F::PPT; ++q)
 #pragma unroll
     for (int o = 0; o < Nqe; ++o)
-      il[q][o] = active ? __ldg(inv_L + (size_t)element * Npe + o * F::Nrows + t + F::TPE * q) : 0.f;
+      il[q][o] = active ? __ldcs(inv_L + (size_t)element * Npe + o * F::Nrows + t + F::TPE * q) : 0.f;
 
   // ---- stage the extended element (natural layout, 16-byte copies) and the S matrices (+ transposes).
   // All global loads of a thread are issued back to back into registers before the first dependent
@@ -126,9 +126,9 @@ __global__ void __launch_bounds__(FdmV1<Nqe>::TPE* EPB)
     for (int n = 0; n < NS; ++n) {
       const int idx = t + n * F::TPE;
       const bool ok = active && idx < Nqe2;
-      rs[0][n] = ok ? __ldg(S_x + (size_t)element * Nqe2 + idx) : 0.f;
-      rs[1][n] = ok ? __ldg(S_y + (size_t)element * Nqe2 + idx) : 0.f;
-      rs[2][n] = ok ? __ldg(S_z + (size_t)element * Nqe2 + idx) : 0.f;
+      rs[0][n] = ok ? __ldcs(S_x + (size_t)element * Nqe2 + idx) : 0.f;
+      rs[1][n] = ok ? __ldcs(S_y + (size_t)element * Nqe2 + idx) : 0.f;
+      rs[2][n] = ok ? __ldcs(S_z + (size_t)element * Nqe2 + idx) : 0.f;
     }
     float4* dst = reinterpret_cast<float4*>(A);
 #pragma unroll

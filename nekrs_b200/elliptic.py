@@ -194,9 +194,13 @@ class Elliptic:
 
 
 class OperatorBench:
-    """The fused operator  Aq = Q Q^T mask (A q)  on a box brick per rank: what bench.py times."""
+    """The fused operator  Aq = Q Q^T mask (A q)  on a box brick per rank: what bench.py times.
 
-    def __init__(self, N, nel_per_rank, *, rank=0, nranks=1, dist=None, seed=1234):
+    `nsets` independent copies of the problem (handle with its own geometric factors, q, Aq) are built and
+    the timed loops rotate over them: one set is 151 MB at E=4096, N=7 (> the 126 MB L2), three sets are
+    453 MB, so every step streams its inputs from HBM without a flush kernel between the steps."""
+
+    def __init__(self, N, nel_per_rank, *, rank=0, nranks=1, dist=None, seed=1234, nsets=3):
         from . import parallel
         self.proc_grid = meshgen.brick_partition(nranks)
         nel = tuple(n * p for n, p in zip(nel_per_rank, self.proc_grid))
@@ -204,25 +208,49 @@ class OperatorBench:
         self.comm = parallel.Comm(dist) if nranks > 1 else None
         topo_of = (lambda ids: parallel.discover_topology(ids, self.comm)) if nranks > 1 else None
         opts = {"SOLVER": "PCG", "PRECONDITIONER": "NONE", "MAXIMUM ITERATIONS": "100", "SOLVER TOLERANCE": "1e-12"}
-        self.elliptic = Elliptic(self.mesh, opts, comm=self.comm, topo_of=topo_of)
         self.Nelements, self.Np = self.mesh.Nelements, self.mesh.Np
-        fo = self.elliptic.fieldOffset
         r = np.random.Generator(np.random.PCG64(seed + rank))
+        self.sets = []
+        for _ in range(nsets):
+            ell = Elliptic(self.mesh, opts, comm=self.comm, topo_of=topo_of)
+            fo = ell.fieldOffset
+            h = np.zeros(fo)
+            h[:self.Nelements * self.Np] = r.random(self.Nelements * self.Np)
+            self.sets.append((ell, DeviceBuffer(like=h), DeviceBuffer.zeros(fo, np.float64)))
+        self.elliptic, self.d_q, self.d_Aq = self.sets[0]
+        fo = self.elliptic.fieldOffset
         self.h_q = lib.PinnedBuffer(fo, np.float64)
         self.h_Aq = lib.PinnedBuffer(fo, np.float64)
-        self.h_q.array[:] = 0
-        self.h_q.array[:self.Nelements * self.Np] = r.random(self.Nelements * self.Np)
-        self.d_q = DeviceBuffer(like=self.h_q.array)
-        self.d_Aq = DeviceBuffer.zeros(fo, np.float64)
+        self.h_q.array[:] = self.d_q.download()
         self.ax_variant = self.elliptic.autotune()[0]
-        self.launches_per_step = 2 if nranks == 1 else (4 if self.elliptic.get_int("overlap") else 4)
+        for ell, _, _ in self.sets[1:]:
+            ell.set_ax_variant(8, self.ax_variant)
+        self.launches_per_step = 2 if nranks == 1 else 4
         self._ev = [lib.Event() for _ in range(3)]
+        self._k = 0
 
     def step(self):
-        self.elliptic.operator(self.d_q, self.d_Aq)
+        ell, q, Aq = self.sets[self._k % len(self.sets)]
+        self._k += 1
+        ell.operator(q, Aq)
+
+    def ax_only(self):
+        ell, q, Aq = self.sets[self._k % len(self.sets)]
+        self._k += 1
+        ell.ax(q, Aq)
+
+    def timed_loop(self, fn, steps):
+        """ms per call of `fn` over `steps` back-to-back calls (one event pair, launching stream)."""
+        e0, e1, _ = self._ev
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        e1.synchronize()
+        return e0.elapsed_ms(e1) / steps
 
     def timed_step(self, flush=True):
-        """(ms for the whole operator, ms for the axhelm launch alone)."""
+        """(ms for the whole operator, ms for the axhelm launch alone), each timed alone after an L2 flush."""
         if flush:
             lib.l2_flush()
         e0, e1, e2 = self._ev
@@ -231,7 +259,6 @@ class OperatorBench:
         e1.record()
         e1.synchronize()
         total = e0.elapsed_ms(e1)
-        # axhelm alone, same cold-L2 conditions
         if flush:
             lib.l2_flush()
         e0.record()
