@@ -11,6 +11,7 @@
 //
 // Same arithmetic order as variant 1 => identical results.
 #include "common.cuh"
+#include "halo.cuh"
 
 namespace nrsb {
 
@@ -67,6 +68,12 @@ __device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, uint32
       "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
       : "memory");
 }
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p)
+{
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ void group_sync(int id, int nthreads)
 {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -93,11 +100,17 @@ struct SlabT {
 
 }  // namespace
 
-template <typename T, int Nq, int NGROUPS, int NSTAGES, bool kPoisson>
-__global__ void __launch_bounds__(NGROUPS* Nq* Nq + 32, 1)
+// kFused: the first F.NhaloElements entries of the element list are the elements that touch another rank.
+// A second service warp waits until all of them are stored (device-scope counter), then packs the halo
+// rows and pushes the partial sums into the neighbours' receive windows over NVLink while the consumer
+// groups carry on with the interior elements: ellipticOperator's "Ax(halo) -> oogs::start -> Ax(interior)"
+// (ellipticOperator.cpp:117-172) in ONE launch.  All CTAs are co-resident (grid <= #SMs, one CTA per SM),
+// so the wait cannot deadlock; it is bounded anyway.
+template <typename T, int Nq, int NGROUPS, int NSTAGES, bool kPoisson, bool kFused>
+__global__ void __launch_bounds__(NGROUPS* Nq* Nq + (kFused ? 64 : 32), 1)
     ax_tma_kernel(const dlong Nelements, const dlong* __restrict__ elementList, const T* __restrict__ ggeo,
                   const DMat<T, Nq> Dm, const T* __restrict__ lambda0, const T* __restrict__ lambda1,
-                  const T* __restrict__ q, T* __restrict__ Aq)
+                  const T* __restrict__ q, T* __restrict__ Aq, const FusedHalo F)
 {
   constexpr int Np = Nq * Nq * Nq;
   constexpr int Nq2 = Nq * Nq;
@@ -127,6 +140,35 @@ __global__ void __launch_bounds__(NGROUPS* Nq* Nq + 32, 1)
   }
   __syncthreads();
 
+  if (kFused && tid >= nConsumers + 32) {
+    // ===== halo service warp =====
+    const int lane = tid - nConsumers - 32;
+    const HaloExchangeDev& H = F.H;
+    if (lane == 0) {
+      const long long t0 = clock64();
+      while (ld_acquire_u64(F.counter) < F.target) {
+        __nanosleep(100);
+        if (clock64() - t0 > (1ll << 33)) break;  // ~4 s: never reached unless co-residency was violated
+      }
+    }
+    __syncwarp();
+    for (int row = blockIdx.x * 32 + lane; row < H.nRows; row += gridDim.x * 32)
+      halo_pack_row<T, true>(H, 1, F.stride, gs_op::add, Aq, (T*)F.partial, row, 0);
+    __threadfence_system();
+    __syncwarp();
+    unsigned ticket = 0;
+    if (lane == 0) ticket = atomicAdd(H.ticket, 1u);
+    ticket = __shfl_sync(0xffffffffu, ticket, 0);
+    if (ticket == gridDim.x - 1) {  // every CTA's rows are out: raise the epoch flag at every peer
+      __threadfence_system();
+      for (int p = lane; p < H.nPeers; p += 32) {
+        volatile unsigned long long* f = H.peerFlags[p] + H.myRank;
+        *f = H.epoch;
+      }
+      if (lane == 0) *H.ticket = 0u;
+    }
+    return;
+  }
   if (tid >= nConsumers) {
     // ===== producer warp: one lane streams element slabs into the ring =====
     if (tid == nConsumers) {
@@ -271,20 +313,23 @@ __global__ void __launch_bounds__(NGROUPS* Nq* Nq + 32, 1)
       if constexpr (!kPoisson) v += r_mass[k];
       Ae[k * Nq2] = v;
     }
+    const bool haloElem = kFused && (blockIdx.x + (dlong)i * gridDim.x < F.NhaloElements);
+    if (haloElem) __threadfence();
     group_sync(1 + g, Nq2);  // su/ss are rewritten by the next element of this group
+    if (haloElem && t == 0) atomicAdd(F.counter, 1ull);
   }
 }
 
-template <typename T, int Nq, int NGROUPS, int NSTAGES, bool kPoisson>
+template <typename T, int Nq, int NGROUPS, int NSTAGES, bool kPoisson, bool kFused = false>
 static int launch_tma(dlong Nelements, const dlong* elementList, const T* ggeo, const T* D_host, const T* lambda0,
-                      const T* lambda1, const T* q, T* Aq, cudaStream_t stream)
+                      const T* lambda1, const T* q, T* Aq, cudaStream_t stream, const FusedHalo* fused = nullptr)
 {
   constexpr int Np = Nq * Nq * Nq;
   constexpr int NG = kPoisson ? 6 : 7;
   using S = SlabT<T, Nq>;
   const size_t smem = ((size_t)NSTAGES * (NG + 1) * Np + (size_t)NGROUPS * 3 * S::size) * sizeof(T) +
                       2 * NSTAGES * sizeof(uint64_t) + 128;
-  auto kern = ax_tma_kernel<T, Nq, NGROUPS, NSTAGES, kPoisson>;
+  auto kern = ax_tma_kernel<T, Nq, NGROUPS, NSTAGES, kPoisson, kFused>;
   static bool configured = false;
   if (!configured) {
     NRSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -294,7 +339,9 @@ static int launch_tma(dlong Nelements, const dlong* elementList, const T* ggeo, 
   for (int n = 0; n < Nq * Nq; ++n) Dm.v[n] = D_host[n];
   int grid = kNumSMs;
   if (grid > Nelements) grid = Nelements;
-  kern<<<grid, NGROUPS * Nq * Nq + 32, smem, stream>>>(Nelements, elementList, ggeo, Dm, lambda0, lambda1, q, Aq);
+  const FusedHalo F = fused ? *fused : FusedHalo();
+  kern<<<grid, NGROUPS * Nq * Nq + (kFused ? 64 : 32), smem, stream>>>(Nelements, elementList, ggeo, Dm, lambda0,
+                                                                        lambda1, q, Aq, F);
   NRSB_CHECK_LAUNCH();
   return NRSB_OK;
 }
@@ -325,6 +372,32 @@ int ax_tma_launch(int Nq, int variant, dlong Nelements, const dlong* elementList
   }
 #undef NRSB_TMA
 }
+
+// Ax over [halo elements..., interior elements...] with the halo push done inside the launch (kFused)
+template <typename T>
+int ax_tma_fused_launch(int Nq, int variant, dlong Nelements, const dlong* elementList, const T* ggeo, const T* D_host,
+                        const T* lambda0, const T* lambda1, int poisson, const T* q, T* Aq, const FusedHalo& F,
+                        cudaStream_t stream)
+{
+  if (Nelements == 0) return NRSB_OK;
+  if (Nq != 8) {
+    set_last_error("fused axhelm + halo push is built for Nq = 8 only");
+    return NRSB_ERR_INVALID;
+  }
+  (void)variant;
+#define NRSB_TMAF(G, S_)                                                                                      \
+  return poisson ? launch_tma<T, 8, G, S_, true, true>(Nelements, elementList, ggeo, D_host, lambda0, lambda1, q, \
+                                                       Aq, stream, &F)                                         \
+                 : launch_tma<T, 8, G, S_, false, true>(Nelements, elementList, ggeo, D_host, lambda0, lambda1, q, \
+                                                        Aq, stream, &F);
+  if (sizeof(T) == 8) { NRSB_TMAF(3, 6) }
+  NRSB_TMAF(6, 12)
+#undef NRSB_TMAF
+}
+template int ax_tma_fused_launch<double>(int, int, dlong, const dlong*, const double*, const double*, const double*,
+                                         const double*, int, const double*, double*, const FusedHalo&, cudaStream_t);
+template int ax_tma_fused_launch<float>(int, int, dlong, const dlong*, const float*, const float*, const float*,
+                                        const float*, int, const float*, float*, const FusedHalo&, cudaStream_t);
 
 template int ax_tma_launch<double>(int, int, dlong, const dlong*, const double*, const double*, const double*,
                                    const double*, int, const double*, double*, cudaStream_t);

@@ -246,7 +246,129 @@ int coarseSolver_t::setup(pMGLevel* lvl, int maxIter_, double tol_)
   if ((rc = s.alloc(NT))) return rc;
   if ((rc = w.alloc(NT))) return rc;
   if ((rc = scal.alloc(C_COUNT))) return rc;
+  if (multiRank && mesh->comm && mesh->comm->nranks > 1 && !e->options.compareArgs("COARSE SOLVER REPLICATED", "FALSE"))
+    if ((rc = setup_replicated(idsT, rowNode, tIndex, rows))) return rc;
   return plan_cluster();
+}
+
+coarseSolver_t::~coarseSolver_t()
+{
+  for (void* b : peerWinBase)
+    if (b && b != (void*)rhsWindow) cudaIpcCloseMemHandle(b);
+  if (rhsWindow) cudaFree(rhsWindow);
+}
+
+// Replicated coarse problem: global numbering of the unique unmasked coarse nodes, the global assembled
+// matrix (every rank's element contributions summed in ascending rank order: identical bits everywhere),
+// who pushes which right-hand-side entry, and the peer-mapped windows the entries are pushed into.
+int coarseSolver_t::setup_replicated(const std::vector<hlong>& idsT, const std::vector<int>& rowNode,
+                                     const std::vector<int>& tIndex, const std::vector<std::map<int, double>>& rows)
+{
+  comm_t* comm = level->elliptic->mesh->comm;
+  const int nr = comm->nranks, me = comm->rank;
+  int rc;
+  // ---- global numbering
+  std::vector<long> counts(nr, 0);
+  counts[me] = NT;
+  comm->allgather_bytes(counts.data(), sizeof(long));
+  long maxNT = 1;
+  for (long c : counts) maxNT = std::max(maxNT, c);
+  std::vector<hlong> allIds((size_t)nr * maxNT, -1);
+  std::copy(idsT.begin(), idsT.end(), allIds.begin() + (size_t)me * maxNT);
+  comm->allgather_bytes(allIds.data(), (size_t)maxNT * sizeof(hlong));
+  std::vector<hlong> G;
+  for (int r = 0; r < nr; ++r) G.insert(G.end(), allIds.begin() + (size_t)r * maxNT, allIds.begin() + (size_t)r * maxNT + counts[r]);
+  std::sort(G.begin(), G.end());
+  G.erase(std::unique(G.begin(), G.end()), G.end());
+  NTg = (int)G.size();
+  auto gidx = [&](hlong id) { return (int)(std::lower_bound(G.begin(), G.end(), id) - G.begin()); };
+  std::vector<int> owner(NTg, -1);
+  for (int r = 0; r < nr; ++r)
+    for (long i = 0; i < counts[r]; ++i) {
+      const int g = gidx(allIds[(size_t)r * maxNT + i]);
+      if (owner[g] < 0) owner[g] = r;
+    }
+  std::vector<int> gOfT(NT), ownG, ownNode;
+  for (int t = 0; t < NT; ++t) {
+    gOfT[t] = gidx(idsT[t]);
+    if (owner[gOfT[t]] == me) {
+      ownG.push_back(gOfT[t]);
+      ownNode.push_back(rowNode[t]);
+    }
+  }
+  nOwn = (int)ownG.size();
+  // ---- global matrix: all-gather the local triplets
+  std::vector<int> tr, tc;
+  std::vector<double> tv;
+  for (int t = 0; t < NT; ++t)
+    for (auto& kv : rows[t]) {
+      tr.push_back(gOfT[t]);
+      tc.push_back(gOfT[kv.first]);
+      tv.push_back(kv.second);
+    }
+  std::vector<long> nnz(nr, 0);
+  nnz[me] = (long)tr.size();
+  comm->allgather_bytes(nnz.data(), sizeof(long));
+  long maxNnz = 1;
+  for (long c : nnz) maxNnz = std::max(maxNnz, c);
+  std::vector<int> allR((size_t)nr * maxNnz, 0), allC((size_t)nr * maxNnz, 0);
+  std::vector<double> allV((size_t)nr * maxNnz, 0.0);
+  std::copy(tr.begin(), tr.end(), allR.begin() + (size_t)me * maxNnz);
+  std::copy(tc.begin(), tc.end(), allC.begin() + (size_t)me * maxNnz);
+  std::copy(tv.begin(), tv.end(), allV.begin() + (size_t)me * maxNnz);
+  comm->allgather_bytes(allR.data(), (size_t)maxNnz * sizeof(int));
+  comm->allgather_bytes(allC.data(), (size_t)maxNnz * sizeof(int));
+  comm->allgather_bytes(allV.data(), (size_t)maxNnz * sizeof(double));
+  std::vector<std::map<int, double>> grow(NTg);
+  for (int r = 0; r < nr; ++r)
+    for (long i = 0; i < nnz[r]; ++i) grow[allR[(size_t)r * maxNnz + i]][allC[(size_t)r * maxNnz + i]] += allV[(size_t)r * maxNnz + i];
+  gEllWidth = 0;
+  for (int g = 0; g < NTg; ++g) gEllWidth = std::max(gEllWidth, (int)grow[g].size());
+  gEllWidth = (gEllWidth + 2) / 3 * 3;
+  std::vector<int> cols((size_t)gEllWidth * NTg);
+  std::vector<float> vals((size_t)gEllWidth * NTg, 0.f), idg(NTg, 0.f);
+  for (int g = 0; g < NTg; ++g) {
+    int k = 0;
+    for (auto& kv : grow[g]) {
+      cols[(size_t)k * NTg + g] = kv.first;
+      vals[(size_t)k * NTg + g] = (float)kv.second;
+      if (kv.first == g) idg[g] = 1.0f / (float)kv.second;
+      ++k;
+    }
+    for (; k < gEllWidth; ++k) cols[(size_t)k * NTg + g] = g;
+  }
+  std::vector<int> tIndexG(tIndex.size());
+  for (size_t n = 0; n < tIndex.size(); ++n) tIndexG[n] = tIndex[n] >= 0 ? gOfT[tIndex[n]] : -1;
+  if ((rc = g_cols.upload(cols))) return rc;
+  if ((rc = g_vals.upload(vals))) return rc;
+  if ((rc = g_invDiag.upload(idg))) return rc;
+  if ((rc = g_tIndex.upload(tIndexG))) return rc;
+  if ((rc = d_ownG.upload(ownG))) return rc;
+  if ((rc = d_ownNode.upload(ownNode))) return rc;
+  // ---- peer-mapped right-hand-side windows
+  const size_t NTpad = ((size_t)NTg + 3) / 4 * 4;
+  const size_t bytes = 2 * NTpad * sizeof(float) + (size_t)nr * sizeof(unsigned long long);
+  NRSB_CUDA(cudaMalloc((void**)&rhsWindow, bytes));
+  NRSB_CUDA(cudaMemset(rhsWindow, 0, bytes));
+  NRSB_CUDA(cudaDeviceSynchronize());
+  std::vector<cudaIpcMemHandle_t> handles(nr);
+  NRSB_CUDA(cudaIpcGetMemHandle(&handles[me], rhsWindow));
+  comm->allgather_bytes(handles.data(), sizeof(cudaIpcMemHandle_t));
+  peerWinBase.assign(nr, nullptr);
+  std::vector<float*> win(nr);
+  std::vector<unsigned long long*> flg(nr);
+  for (int p = 0; p < nr; ++p) {
+    void* base = rhsWindow;
+    if (p != me) NRSB_CUDA(cudaIpcOpenMemHandle(&base, handles[p], cudaIpcMemLazyEnablePeerAccess));
+    peerWinBase[p] = base;
+    win[p] = (float*)base;
+    flg[p] = (unsigned long long*)((float*)base + 2 * NTpad);
+  }
+  if ((rc = d_peerWin.upload(win))) return rc;
+  if ((rc = d_peerWinFlags.upload(flg))) return rc;
+  comm->barrier();
+  replicated = true;
+  return NRSB_OK;
 }
 
 int coarseSolver_t::variant = 1;
@@ -292,7 +414,7 @@ int coarseSolver_t::solve(float* rhs, float* xE)
   const int grid = (NT + kBlockSize - 1) / kBlockSize;
   double* S = scal.p;
   int rc;
-  if (variant == 1 && clusterSize > 0) return solve_cluster(rhs, xE);
+  if (variant == 1 && clusterSize > 0 && (!multiRank || replicated)) return solve_cluster(rhs, xE);
   iterOnDevice = false;
   lastIter = 0;
   if (NT > 0) {

@@ -10,7 +10,14 @@
 //     partials likewise; `cluster.sync()` (~0.2 us) replaces the kernel boundary;
 //   * alpha/beta and the convergence test are evaluated redundantly by every thread (same bits).
 // Same recurrences, same SpMV summation order and the same `checkEvery` convergence test as the
-// multi-launch path in coarse.cu (which remains the path for several ranks / larger coarse grids).
+// multi-launch path in coarse.cu.
+//
+// Several ranks: the coarse problem is REPLICATED.  Every GPU holds the global assembled matrix; the
+// kernel prologue all-gathers the right-hand side (each rank stores the entries it owns straight into
+// every peer's window over NVLink, then raises an epoch flag), after which all GPUs run the identical
+// solve on identical data and keep their own part of the solution.  One exchange per coarse solve
+// instead of two per Krylov iteration.  When two copies of the vector no longer fit in shared memory
+// the SpMV input goes through a global (L2-resident) buffer instead of distributed shared memory.
 #include <cooperative_groups.h>
 
 #include "host.hpp"
@@ -39,6 +46,19 @@ struct ClusterArgs {
   double tol2;
   int matInSmem;
   double* S;  // [0]=gamma, [1]=gamma0, [2]=iterations
+  // SpMV input in global memory instead of distributed shared memory (large coarse grids)
+  int uGlobal;
+  float* uScratch;  // [2][NTpad]
+  // replicated multi-rank solve: right-hand-side all-gather through peer windows
+  int nranks, myRank;
+  int nOwn;
+  const int* ownG;     // global T index of the entries this rank owns
+  const int* ownNode;  // E-vector node holding the value
+  float* const* peerWin;                   // [nranks] windows: float[2][NTpad]
+  unsigned long long* const* peerFlags;    // [nranks] flag arrays u64[nranks]
+  const float* myWin;
+  const unsigned long long* myFlags;
+  unsigned long long epoch;
 };
 
 __device__ __forceinline__ double warp_sum_d(double v)
@@ -59,8 +79,9 @@ __global__ void __launch_bounds__(kCThreads, 1) coarse_pcg_cluster_kernel(const 
   extern __shared__ __align__(16) unsigned char smraw[];
   double* red = reinterpret_cast<double*>(smraw);       // [2][kMaxCluster][2]  (written by peers)
   double* wred = red + 2 * kMaxCluster * 2;             // [32 warps][2]
-  float* ubuf = reinterpret_cast<float*>(wred + 64);    // [2][NTpad]           (written by peers)
-  float* mvals = ubuf + 2 * (size_t)a.NTpad;            // [W][RPC]
+  float* ubufS = reinterpret_cast<float*>(wred + 64);   // [2][NTpad]           (written by peers)
+  float* mvals = ubufS + (a.uGlobal ? 0 : 2 * (size_t)a.NTpad);  // [W][RPC]
+  float* ubuf = a.uGlobal ? a.uScratch : ubufS;
   int* mcols = reinterpret_cast<int*>(mvals + (size_t)a.W * a.RPC);
 
   const int row0 = c * a.RPC;
@@ -87,6 +108,31 @@ __global__ void __launch_bounds__(kCThreads, 1) coarse_pcg_cluster_kernel(const 
     moff = row0;
   }
 
+  // several ranks: all-gather the right-hand side (every rank pushes what it owns to everybody)
+  const float* bsrc = nullptr;
+  if (a.nranks > 1) {
+    const size_t woff = (size_t)(a.epoch & 1ull) * a.NTpad;
+    for (int i = c * kCThreads + tid; i < a.nOwn; i += C * kCThreads) {
+      const float v = a.rhsE[a.ownNode[i]];
+      const int g = a.ownG[i];
+      for (int pr = 0; pr < a.nranks; ++pr) a.peerWin[pr][woff + g] = v;  // NVLink stores (own window included)
+    }
+    __threadfence_system();
+    cluster.sync();
+    if (c == 0 && tid < a.nranks) {
+      volatile unsigned long long* f = a.peerFlags[tid] + a.myRank;
+      *f = a.epoch;
+    }
+    if (tid < a.nranks) {
+      const volatile unsigned long long* f = a.myFlags + tid;
+      while (*f < a.epoch) {
+      }
+    }
+    __syncthreads();
+    __threadfence_system();
+    bsrc = a.myWin + woff;
+  }
+
   float x[RMAX], r[RMAX], u[RMAX], p[RMAX], s[RMAX], w[RMAX], idg[RMAX], wgt[RMAX];
   bool own[RMAX];
 #pragma unroll
@@ -94,9 +140,9 @@ __global__ void __launch_bounds__(kCThreads, 1) coarse_pcg_cluster_kernel(const 
     const int lr = tid + j * kCThreads;
     own[j] = lr < nRows;
     const int g = row0 + lr;
-    const float b = own[j] ? a.rhsE[a.rowNode[g]] : 0.f;
+    const float b = own[j] ? (bsrc ? __ldcg(bsrc + g) : a.rhsE[a.rowNode[g]]) : 0.f;
     idg[j] = own[j] ? a.invDiag[g] : 0.f;
-    wgt[j] = own[j] ? a.weight[g] : 0.f;
+    wgt[j] = own[j] ? (a.weight ? a.weight[g] : 1.f) : 0.f;
     x[j] = 0.f;
     r[j] = b;
     u[j] = idg[j] * b;
@@ -118,17 +164,26 @@ __global__ void __launch_bounds__(kCThreads, 1) coarse_pcg_cluster_kernel(const 
     for (int j = 0; j < RMAX; ++j)
       if (own[j]) {
         const int g = row0 + tid + j * kCThreads;
-        for (int q = 0; q < C; ++q) cluster.map_shared_rank(ub, q)[g] = u[j];
+        if (a.uGlobal) {
+          ub[g] = u[j];
+        } else {
+          for (int q = 0; q < C; ++q) cluster.map_shared_rank(ub, q)[g] = u[j];
+        }
       }
-    cluster.sync();
+    cluster.sync();  // release/acquire at cluster scope: orders the global stores as well
     double pg = 0.0, pd = 0.0;
 #pragma unroll
     for (int j = 0; j < RMAX; ++j)
       if (own[j]) {
         const int lr = tid + j * kCThreads;
         float acc = 0.f;
-        for (int k = 0; k < a.W; ++k)  // ascending column, as the multi-launch path
-          acc += mv[(size_t)k * mstride + moff + lr] * ub[mc[(size_t)k * mstride + moff + lr]];
+        if (a.uGlobal) {
+          for (int k = 0; k < a.W; ++k)
+            acc += mv[(size_t)k * mstride + moff + lr] * __ldcg(ub + mc[(size_t)k * mstride + moff + lr]);
+        } else {
+          for (int k = 0; k < a.W; ++k)  // ascending column, as the multi-launch path
+            acc += mv[(size_t)k * mstride + moff + lr] * ub[mc[(size_t)k * mstride + moff + lr]];
+        }
         w[j] = acc;
         const double ut = (double)u[j], wg = (double)wgt[j];
         pg += (double)r[j] * ut * wg;
@@ -198,13 +253,17 @@ __global__ void __launch_bounds__(kCThreads, 1) coarse_pcg_cluster_kernel(const 
     for (int j = 0; j < RMAX; ++j)
       if (own[j]) {
         const int g = row0 + tid + j * kCThreads;
-        for (int q = 0; q < C; ++q) cluster.map_shared_rank(xb, q)[g] = x[j];
+        if (a.uGlobal) {
+          xb[g] = x[j];
+        } else {
+          for (int q = 0; q < C; ++q) cluster.map_shared_rank(xb, q)[g] = x[j];
+        }
       }
     cluster.sync();
     const long stride = (long)C * kCThreads;
     for (long n = (long)c * kCThreads + tid; n < a.Nlocal; n += stride) {
       const int t = a.tIndex[n];
-      a.xE[n] = (t >= 0) ? xb[t] : 0.f;
+      a.xE[n] = (t >= 0) ? (a.uGlobal ? __ldcg(xb + t) : xb[t]) : 0.f;
     }
   }
   if (c == 0 && tid == 0) {
@@ -255,40 +314,51 @@ int dispatch_cluster(const ClusterArgs& a, int C, int rmax, size_t smem, cudaStr
     case 1: return launch_cluster<1>(a, C, smem, st, queryOnly);
     case 2: return launch_cluster<2>(a, C, smem, st, queryOnly);
     case 4: return launch_cluster<4>(a, C, smem, st, queryOnly);
+    case 8: return launch_cluster<8>(a, C, smem, st, queryOnly);
     default: return 1;
   }
 }
 
 }  // namespace
 
-// Picks the cluster shape at setup.  Leaves clusterSize = 0 when the coarse grid does not fit.
+// Picks the cluster shape at setup for a system of `n` rows.  Leaves clusterSize = 0 when nothing fits.
 int coarseSolver_t::plan_cluster()
 {
   clusterSize = 0;
-  if (multiRank || NT <= 0) return NRSB_OK;
+  const int n = replicated ? NTg : NT;
+  if ((multiRank && !replicated) || n <= 0) return NRSB_OK;
   const size_t limit = 227 * 1024;
-  const int NTpad = (NT + 3) / 4 * 4;
+  const int NTpad = (n + 3) / 4 * 4;
   for (int C : {16, 8}) {
-    const int RPC = ((NT + C - 1) / C + 31) / 32 * 32;
+    const int RPC = ((n + C - 1) / C + 31) / 32 * 32;
     int rmax = (RPC + kCThreads - 1) / kCThreads;
     if (rmax == 3) rmax = 4;
-    if (rmax > 4) continue;
-    const size_t base = (2 * kMaxCluster * 2 + 64) * sizeof(double) + 2 * (size_t)NTpad * sizeof(float);
-    const size_t mat = (size_t)ellWidth * RPC * 8;
-    int inSmem = 1;
-    size_t smem = base + mat;
-    if (smem > limit) {
-      inSmem = 0;
-      smem = base;
+    if (rmax > 4 && rmax <= 8) rmax = 8;
+    if (rmax > 8) continue;
+    const size_t fixed = (2 * kMaxCluster * 2 + 64) * sizeof(double);
+    const size_t uBytes = 2 * (size_t)NTpad * sizeof(float);
+    const size_t mat = (size_t)(replicated ? gEllWidth : ellWidth) * RPC * 8;
+    // preference: everything in shared memory; then the matrix from L2; then the vector from L2 as well
+    const int tryU[3] = {0, 0, 1}, tryM[3] = {1, 0, 0};
+    int pick = -1;
+    size_t smem = 0;
+    for (int o = 0; o < 3 && pick < 0; ++o) {
+      smem = fixed + (tryU[o] ? 0 : uBytes) + (tryM[o] ? mat : 0);
+      if (smem <= limit) pick = o;
     }
-    if (smem > limit) continue;
+    if (pick < 0) continue;
     ClusterArgs a = {};
     if (dispatch_cluster(a, C, rmax, smem, nullptr, true) != 0) continue;
     clusterSize = C;
     clusterRPC = RPC;
     clusterRmax = rmax;
     clusterSmem = smem;
-    clusterMatInSmem = inSmem;
+    clusterMatInSmem = tryM[pick];
+    clusterUGlobal = tryU[pick];
+    if (clusterUGlobal) {
+      int rc = uScratch.alloc(2 * (size_t)NTpad);
+      if (rc) return rc;
+    }
     break;
   }
   return NRSB_OK;
@@ -297,17 +367,18 @@ int coarseSolver_t::plan_cluster()
 int coarseSolver_t::solve_cluster(float* rhs, float* xE)
 {
   elliptic_t* e = level->elliptic;
-  ClusterArgs a;
-  a.NT = NT;
-  a.W = ellWidth;
+  ClusterArgs a = {};
+  const int n = replicated ? NTg : NT;
+  a.NT = n;
+  a.W = replicated ? gEllWidth : ellWidth;
   a.RPC = clusterRPC;
-  a.NTpad = (NT + 3) / 4 * 4;
-  a.cols = d_cols.p;
-  a.vals = d_vals.p;
-  a.invDiag = invDiag.p;
-  a.weight = d_weight.p;
+  a.NTpad = (n + 3) / 4 * 4;
+  a.cols = replicated ? g_cols.p : d_cols.p;
+  a.vals = replicated ? g_vals.p : d_vals.p;
+  a.invDiag = replicated ? g_invDiag.p : invDiag.p;
+  a.weight = replicated ? nullptr : d_weight.p;
   a.rowNode = d_rowNode.p;
-  a.tIndex = d_tIndex.p;
+  a.tIndex = replicated ? g_tIndex.p : d_tIndex.p;
   a.rhsE = rhs;
   a.xE = xE;
   a.Nlocal = e->mesh->Nlocal;
@@ -316,6 +387,21 @@ int coarseSolver_t::solve_cluster(float* rhs, float* xE)
   a.tol2 = tol * tol;
   a.matInSmem = clusterMatInSmem;
   a.S = scal.p + 8;
+  a.uGlobal = clusterUGlobal;
+  a.uScratch = uScratch.p;
+  a.nranks = 1;
+  if (replicated) {
+    a.nranks = e->mesh->comm->nranks;
+    a.myRank = e->mesh->comm->rank;
+    a.nOwn = nOwn;
+    a.ownG = d_ownG.p;
+    a.ownNode = d_ownNode.p;
+    a.peerWin = d_peerWin.p;
+    a.peerFlags = d_peerWinFlags.p;
+    a.myWin = rhsWindow;
+    a.myFlags = (const unsigned long long*)(rhsWindow + 2 * (size_t)a.NTpad);
+    a.epoch = ++winEpoch;
+  }
   iterOnDevice = true;
   return dispatch_cluster(a, clusterSize, clusterRmax, clusterSmem, e->stream, false);
 }

@@ -18,6 +18,7 @@
 #include <cstring>
 
 #include "host.hpp"
+#include "halo.cuh"
 #include "projection.hpp"
 
 namespace nrsb {
@@ -173,6 +174,20 @@ int ellipticOperator(elliptic_t* elliptic, const T* o_q, T* o_Aq, bool masked)
   oogs_t* oogs = elliptic->oogs.get();
   int rc;
   const dlong nm = masked ? elliptic->Nmasked : 0;
+  using P = prec_traits<T>;
+  if (elliptic->overlap && elliptic->fusedHaloAx && mesh->Nq == 8 && elliptic->Nfields == 1 &&
+      elliptic->ax_variant[P::idx] != 0 && mesh->NglobalGatherElements > 0 && oogs->peers.size() <= 32) {
+    // ONE launch: Ax over [halo elements, interior elements]; a service warp per CTA pushes the halo partial
+    // sums over NVLink as soon as the halo elements are stored.  The mask moves to finish (masked nodes
+    // belong to no row of the masked handle, so it commutes with every sum).
+    FusedHalo F;
+    if ((rc = oogs->begin_fused(&F, mesh->NglobalGatherElements, elliptic->fieldOffset))) return rc;
+    if ((rc = ax_tma_fused_launch<T>(mesh->Nq, 5, mesh->Nelements, mesh->o_haloFirstElementList.p, P::ggeo(mesh),
+                                     P::D(mesh), P::lambda0(elliptic), P::lambda1(elliptic), elliptic->poisson ? 1 : 0,
+                                     o_q, o_Aq, F, elliptic->stream)))
+      return rc;
+    return oogs->finish<T>(o_Aq, 1, elliptic->fieldOffset, gs_op::add, nm, elliptic->o_maskIds.p, elliptic->stream);
+  }
   if (elliptic->overlap) {
     if ((rc = ellipticAx<T>(elliptic, mesh->NglobalGatherElements, mesh->o_globalGatherElementList.p, o_q, o_Aq)))
       return rc;
@@ -326,6 +341,7 @@ int ellipticSolveSetup(elliptic_t* elliptic)
 
   // ENABLE GS COMM OVERLAP: the reference times both variants and keeps the faster
   // (ellipticSetup.cpp:278-302).  Splitting only pays when there are halo rows.
+  elliptic->fusedHaloAx = !options.compareArgs("FUSED HALO AX", "FALSE");
   elliptic->overlap = elliptic->ogs->NhaloGather > 0 && !options.compareArgs("ENABLE GS COMM OVERLAP", "FALSE") &&
                       mesh->NlocalGatherElements > 0;
 

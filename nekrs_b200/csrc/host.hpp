@@ -111,6 +111,9 @@ class oogs_t {
   dbuf<double> d_partial;  // per halo row partial sums (k fields)
   cudaStream_t commStream = nullptr;
   cudaEvent_t evStart = nullptr, evDone = nullptr;
+  // fused axhelm + halo push (axhelm_tma.cu): finished-halo-element counter, never reset
+  dbuf<unsigned long long> fusedCounter;
+  unsigned long long fusedTarget = 0;
 
   ~oogs_t();
   int setup(ogs_t* ogs, comm_t* comm, int maxFields);
@@ -120,6 +123,9 @@ class oogs_t {
   int start(T* v, int k, dlong stride, gs_op op, cudaStream_t stream);
   template <typename T>
   int finish(T* v, int k, dlong stride, gs_op op, dlong Nmasked, const dlong* maskIds, cudaStream_t stream);
+  // start() without the pack launch: advances the epoch and describes the exchange to a kernel that
+  // performs the pack itself once `NhaloElements` more elements have been counted (struct FusedHalo, halo.cuh)
+  int begin_fused(struct FusedHalo* F, dlong NhaloElements, dlong stride);
   template <typename T>
   int startFinish(T* v, int k, dlong stride, gs_op op, dlong Nmasked, const dlong* maskIds, cudaStream_t stream)
   {
@@ -145,6 +151,7 @@ class mesh_t {
   dbuf<double> o_ggeo;
   dbuf<float> o_ggeoPfloat;
   dbuf<dlong> o_elementList, o_globalGatherElementList, o_localGatherElementList;
+  dbuf<dlong> o_haloFirstElementList;  // globalGather elements followed by localGather elements
   dlong NglobalGatherElements = 0, NlocalGatherElements = 0;
   std::vector<dlong> globalGatherElementList, localGatherElementList;
   std::unique_ptr<ogs_t> ogs;    // unmasked
@@ -247,8 +254,22 @@ class coarseSolver_t {
   int lastIter = 0;
   bool iterOnDevice = false;
   // single-kernel cluster path (coarse_cluster.cu); clusterSize == 0 -> multi-launch path
-  int clusterSize = 0, clusterRPC = 0, clusterRmax = 0, clusterMatInSmem = 0;
+  int clusterSize = 0, clusterRPC = 0, clusterRmax = 0, clusterMatInSmem = 0, clusterUGlobal = 0;
   size_t clusterSmem = 0;
+  dbuf<float> uScratch;
+  // several ranks: replicated global coarse problem for the cluster kernel (coarse_cluster.cu header)
+  bool replicated = false;
+  int NTg = 0, gEllWidth = 0, nOwn = 0;
+  dbuf<int> g_cols, g_tIndex, d_ownG, d_ownNode;
+  dbuf<float> g_vals, g_invDiag;
+  float* rhsWindow = nullptr;  // float[2][NTgpad] + u64 flags[nranks], peer-mapped
+  std::vector<void*> peerWinBase;
+  dbuf<float*> d_peerWin;
+  dbuf<unsigned long long*> d_peerWinFlags;
+  unsigned long long winEpoch = 0;
+  int setup_replicated(const std::vector<hlong>& idsT, const std::vector<int>& rowNode,
+                       const std::vector<int>& tIndex, const std::vector<std::map<int, double>>& rows);
+  ~coarseSolver_t();
   static int variant;  // 1 (default): cluster kernel when it fits; 0: always the multi-launch path
   int setup(pMGLevel* lvl, int maxIter, double tol);
   int solve(float* rhs, float* x);
@@ -289,6 +310,7 @@ class elliptic_t {
   std::unique_ptr<ogs_t> ogs;
   std::unique_ptr<oogs_t> oogs;
   bool overlap = false;  // oogsAx != oogs in the reference: split Ax into halo / interior elements
+  bool fusedHaloAx = true;  // overlap through ONE launch (axhelm + in-kernel halo push) when Nq == 8
   dlong Nmasked = 0, NmaskedLocal = 0, NmaskedGlobal = 0;
   dbuf<dlong> o_maskIds, o_maskIdsLocal, o_maskIdsGlobal;
   std::vector<dlong> maskIds;

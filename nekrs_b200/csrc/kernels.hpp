@@ -10,6 +10,11 @@ int ax_launch(int Nq, int variant, dlong Nelements, dlong loffset, const dlong* 
               const T* D_host, const T* lambda0, const T* lambda1, int poisson, int lambdaField, const T* q, T* Aq,
               cudaStream_t stream);
 int ax_default_variant(int Nq, int precision);
+struct FusedHalo;
+template <typename T>
+int ax_tma_fused_launch(int Nq, int variant, dlong Nelements, const dlong* elementList, const T* ggeo, const T* D_host,
+                        const T* lambda0, const T* lambda1, int poisson, const T* q, T* Aq, const FusedHalo& F,
+                        cudaStream_t stream);
 
 // fdm.cu
 int fused_fdm_launch(int Nq, int restrict_, dlong Nelements, const dlong* elementList, float* Su, const float* Sx,

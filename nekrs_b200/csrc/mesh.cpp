@@ -71,6 +71,7 @@ template struct dbuf<int>;
 template struct dbuf<unsigned>;
 template struct dbuf<unsigned long long>;
 template struct dbuf<double*>;
+template struct dbuf<float*>;
 template struct dbuf<unsigned long long*>;
 template struct dbuf<void*>;
 template struct dbuf<long>;
@@ -289,6 +290,11 @@ int mesh_t::setup(int N_, dlong Nelements_, const double* x_, const double* y_, 
   if ((rc = o_elementList.upload(elist))) return rc;
   if ((rc = o_globalGatherElementList.upload(globalGatherElementList))) return rc;
   if ((rc = o_localGatherElementList.upload(localGatherElementList))) return rc;
+  {
+    std::vector<dlong> both(globalGatherElementList);
+    both.insert(both.end(), localGatherElementList.begin(), localGatherElementList.end());
+    if ((rc = o_haloFirstElementList.upload(both))) return rc;
+  }
   return NRSB_OK;
 }
 

@@ -22,39 +22,10 @@
 #include <cstring>
 #include <map>
 
+#include "halo.cuh"
 #include "host.hpp"
 
 namespace nrsb {
-
-struct HaloExchangeDev {
-  int nRows;
-  const int* rowStarts;  // local copies CSR
-  const int* rowIds;
-  const int* sendStarts;  // per row: destinations
-  const int* sendPeer;    // peer index
-  const int* sendSlot;    // slot inside my block of that peer's window
-  const int* recvStarts;  // per row: contributions in ascending rank order
-  const int* recvPeer;    // peer index or -1 for the own partial
-  const int* recvSlot;
-  int nPeers;
-  const long* peerRemoteOffset;  // my block's offset (slots) in peer's window
-  const long* peerRecvOffset;    // peer's block offset (slots) in my window
-  const int* peerCount;          // shared rows with peer
-  const int* peerRank;
-  void* const* peerWindow;  // this parity
-  void* myWindow;           // this parity
-  unsigned long long* const* peerFlags;
-  unsigned long long* myFlags;
-  unsigned* ticket;
-  int myRank;
-  unsigned long long epoch;
-};
-
-template <typename T>
-__device__ __forceinline__ T gs_combine(T a, T b, gs_op op)
-{
-  return op == gs_op::add ? a + b : (op == gs_op::min ? (b < a ? b : a) : (b > a ? b : a));
-}
 
 template <typename T>
 __global__ void __launch_bounds__(kBlockSize)
@@ -62,19 +33,7 @@ __global__ void __launch_bounds__(kBlockSize)
                      T* __restrict__ partial)
 {
   const long gid = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid < (long)H.nRows * k) {
-    const int row = gid % H.nRows;
-    const int f = gid / H.nRows;
-    const int s0 = H.rowStarts[row], s1 = H.rowStarts[row + 1];
-    T s = v[H.rowIds[s0] + (size_t)f * stride];
-    for (int c = s0 + 1; c < s1; ++c) s = gs_combine(s, v[H.rowIds[c] + (size_t)f * stride], op);
-    partial[(size_t)f * H.nRows + row] = s;
-    for (int d = H.sendStarts[row]; d < H.sendStarts[row + 1]; ++d) {
-      const int p = H.sendPeer[d];
-      T* w = (T*)H.peerWindow[p];
-      w[(size_t)H.peerRemoteOffset[p] * k + (size_t)f * H.peerCount[p] + H.sendSlot[d]] = s;  // NVLink store
-    }
-  }
+  if (gid < (long)H.nRows * k) halo_pack_row<T>(H, k, stride, op, v, partial, (int)(gid % H.nRows), (int)(gid / H.nRows));
   // publish: every block fences its remote stores, the last one raises the flags
   __shared__ bool last;
   __threadfence_system();
@@ -405,6 +364,27 @@ int oogs_t::start(T* v, int k, dlong stride, gs_op op, cudaStream_t stream)
   halo_pack_kernel<T><<<(unsigned)((total + kBlockSize - 1) / kBlockSize), kBlockSize, 0, stream>>>(
       H, k, stride, op, v, (T*)d_partial.p);
   NRSB_CHECK_LAUNCH();
+  return NRSB_OK;
+}
+
+int oogs_t::begin_fused(FusedHalo* F, dlong NhaloElements, dlong stride)
+{
+  NRSB_REQUIRE(ogs && ogs->NhaloGather > 0, "begin_fused: no halo rows");
+  NRSB_REQUIRE((int)peers.size() <= 32, "begin_fused: too many neighbour ranks");
+  oogs_dev_t* d = g_dev[this].get();
+  if (!fusedCounter.p) {
+    int rc = fusedCounter.alloc(1);
+    if (rc) return rc;
+    NRSB_CUDA(cudaMemset(fusedCounter.p, 0, sizeof(unsigned long long)));
+  }
+  ++epoch;
+  fusedTarget += (unsigned long long)NhaloElements;
+  F->H = make_dev(this, d, (int)(epoch & 1ull));
+  F->NhaloElements = NhaloElements;
+  F->counter = fusedCounter.p;
+  F->target = fusedTarget;
+  F->partial = d_partial.p;
+  F->stride = stride;
   return NRSB_OK;
 }
 

@@ -53,7 +53,7 @@ def pressure_options(**kw) -> dict:
         "MULTIGRID CHEBYSHEV MAX EIGENVALUE BOUND FACTOR": "1.1",
         "MULTIGRID COARSE SOLVE": "TRUE",
         "COARSE SOLVER": "JPCG",
-        "COARSE SOLVER TOLERANCE": "1e-3",
+        "COARSE SOLVER TOLERANCE": "1e-1",
         "COARSE SOLVER MAXIMUM ITERATIONS": "200",
         "INITIAL GUESS": "PREVIOUS",
     }

@@ -628,7 +628,7 @@ class OSolver:
         self.coarse = None
         if coarse_solve:
             self.coarse = CoarseJPCG(self.orc, self.levels[-1], int(o.get("COARSE SOLVER MAXIMUM ITERATIONS", 200)),
-                                     float(o.get("COARSE SOLVER TOLERANCE", 1e-3)))
+                                     float(o.get("COARSE SOLVER TOLERANCE", 1e-1)))
         self.and_smooth = and_smooth
 
     # ---- V-cycle (MGSolver.cpp:167-193)

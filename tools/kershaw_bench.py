@@ -25,7 +25,7 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--bp5-iters", type=int, default=1000)
     ap.add_argument("--smoother", default="FOURTHOPTCHEBYSHEV+RAS")
-    ap.add_argument("--coarse-tol", default="1e-3")
+    ap.add_argument("--coarse-tol", default="1e-1")
     ap.add_argument("--skip-bp5", action="store_true")
     ap.add_argument("--skip-bps5", action="store_true")
     ap.add_argument("--out", default="")

@@ -84,6 +84,20 @@ def main():
         ell.operator(d_q, d_Aq)
     err = np.max(np.abs(d_Aq.download()[:nloc] - out_ref[gnode])) / np.max(np.abs(out_ref))
     report("fused operator (overlap) vs oracle", err < 1e-12, "relerr %.2e" % err)
+    # the single-launch path (axhelm with the in-kernel NVLink halo push) against the split path
+    # (Ax halo -> mask -> oogs::start -> Ax interior -> oogs::finish): same sums, same order => same bits
+    opts_split = dict(opts)
+    opts_split["FUSED HALO AX"] = "FALSE"
+    ell_split = Elliptic(part, opts_split, comm=comm, topo_of=topo_of)
+    d_Aq2 = DB.zeros(ell.fieldOffset, np.float64)
+    for rep in range(3):
+        ell_split.operator(d_q, d_Aq2)
+    same = np.array_equal(d_Aq2.download()[:nloc], d_Aq.download()[:nloc])
+    report("in-kernel halo push == split path", same)
+    for rep in range(200):  # epochs, counters, parity buffers under back-to-back launches
+        ell.operator(d_q, d_Aq)
+    report("fused operator after 200 launches", np.array_equal(d_Aq2.download()[:nloc], d_Aq.download()[:nloc]))
+    ell_split.destroy()
     rhs_glob = meshgen.kershaw_rhs(whole)
     ref.solve(rhs_glob, np.zeros_like(rhs_glob))
     x = np.zeros(nloc)
