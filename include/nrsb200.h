@@ -131,7 +131,9 @@ int nrsb_fusedFDM(int Nq, int restrict_, nrsb_dlong Nelements, const nrsb_dlong*
 int nrsb_set_fdm_variant(int variant);
 /* coarse-grid solve variant (stands where coarseLevel_t::solve calls BoomerAMG, MG/coarseLevel.cpp:182-222):
  * 1 = whole PCG solve in one thread-block-cluster kernel when the coarse grid fits (default, one rank),
- * 0 = two launches per iteration (the path for several ranks) */
+ * 0 = two launches per iteration,
+ * 2 = as 1 but with the SpMV input in an L2-resident global buffer instead of distributed shared memory
+ *     (what large coarse grids fall back to; selectable so that tests can cover it; set before setup) */
 int nrsb_set_coarse_variant(int variant);
 int nrsb_postFDM(int Nq, nrsb_dlong Nelements, float* d_work1, float* d_work2, float* d_Su, const float* d_wts,
                  void* stream);

@@ -101,13 +101,15 @@ struct SlabT {
 }  // namespace
 
 // kFused: the first F.NhaloElements entries of the element list are the elements that touch another rank.
-// A second service warp waits until all of them are stored (device-scope counter), then packs the halo
-// rows and pushes the partial sums into the neighbours' receive windows over NVLink while the consumer
-// groups carry on with the interior elements: ellipticOperator's "Ax(halo) -> oogs::start -> Ax(interior)"
-// (ellipticOperator.cpp:117-172) in ONE launch.  All CTAs are co-resident (grid <= #SMs, one CTA per SM),
-// so the wait cannot deadlock; it is bounded anyway.
+// The last F.nPush CTAs of the grid take no elements: they wait until all halo elements are stored
+// (device-scope counter), then pack the halo rows and push the partial sums into the neighbours' receive
+// windows over NVLink while the other CTAs carry on with the interior elements: ellipticOperator's
+// "Ax(halo) -> oogs::start -> Ax(interior)" (ellipticOperator.cpp:117-172) in ONE launch.  All CTAs are
+// co-resident (grid = #SMs, one CTA per SM), so the wait cannot deadlock; it is bounded anyway.
+// (Measured: a service warp inside a working CTA needs ~20 us for the push, each dependent access queues
+// behind that SM's 200 KB of in-flight bulk copies; dedicated CTAs need ~5 us.)
 template <typename T, int Nq, int NGROUPS, int NSTAGES, bool kPoisson, bool kFused>
-__global__ void __launch_bounds__(NGROUPS* Nq* Nq + (kFused ? 64 : 32), 1)
+__global__ void __launch_bounds__(NGROUPS* Nq* Nq + 32, 1)
     ax_tma_kernel(const dlong Nelements, const dlong* __restrict__ elementList, const T* __restrict__ ggeo,
                   const DMat<T, Nq> Dm, const T* __restrict__ lambda0, const T* __restrict__ lambda1,
                   const T* __restrict__ q, T* __restrict__ Aq, const FusedHalo F)
@@ -129,7 +131,12 @@ __global__ void __launch_bounds__(NGROUPS* Nq* Nq + (kFused ? 64 : 32), 1)
 
   const int tid = threadIdx.x;
   constexpr int nConsumers = NGROUPS * Nq2;
-  const int myCount = (Nelements > (dlong)blockIdx.x) ? (int)((Nelements - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+  // kFused: the last F.nPush CTAs do no element work at all, they are the halo pushers (a CTA whose SM is
+  // saturated by the TMA ring pays microseconds per dependent load; an otherwise idle SM does not)
+  const int nAx = kFused ? (int)gridDim.x - F.nPush : (int)gridDim.x;
+  const bool pusher = kFused && (int)blockIdx.x >= nAx;
+  const int myCount =
+      (!pusher && Nelements > (dlong)blockIdx.x) ? (int)((Nelements - blockIdx.x + nAx - 1) / nAx) : 0;
 
   if (tid == 0) {
     for (int s = 0; s < NSTAGES; ++s) {
@@ -140,32 +147,36 @@ __global__ void __launch_bounds__(NGROUPS* Nq* Nq + (kFused ? 64 : 32), 1)
   }
   __syncthreads();
 
-  if (kFused && tid >= nConsumers + 32) {
-    // ===== halo service warp =====
-    const int lane = tid - nConsumers - 32;
+  if (pusher) {
+    // ===== halo pusher CTA: all threads =====
     const HaloExchangeDev& H = F.H;
-    if (lane == 0) {
+    const int pb = blockIdx.x - nAx;
+    // the send table does not depend on the results: fetch the first batch while the halo elements are
+    // still being computed
+    // the send table does not depend on the results: fetch this thread's entries while the halo elements
+    // are still being computed.  Under a streaming load every dependent access costs 2-3 us (measured), so
+    // after the wait only  value load -> NVLink store -> fence -> flag  remains on the critical path.
+    const int estride = F.nPush * blockDim.x;
+    const int e00 = pb * blockDim.x + tid;
+    HaloSendBatch<16> first;
+    halo_pack_load<16>(H, e00, estride, first);
+    if (tid == 0) {
       const long long t0 = clock64();
       while (ld_acquire_u64(F.counter) < F.target) {
-        __nanosleep(100);
+        __nanosleep(64);
         if (clock64() - t0 > (1ll << 33)) break;  // ~4 s: never reached unless co-residency was violated
       }
     }
-    __syncwarp();
-    for (int row = blockIdx.x * 32 + lane; row < H.nRows; row += gridDim.x * 32)
-      halo_pack_row<T, true>(H, 1, F.stride, gs_op::add, Aq, (T*)F.partial, row, 0);
+    __syncthreads();
+    halo_pack_store<T, 16, true>(H, gs_op::add, Aq, (T*)F.partial, e00, estride, first);
+    for (int e0 = e00 + 16 * estride; e0 < H.nSend; e0 += 8 * estride)
+      halo_pack_flat<T, 8, true>(H, gs_op::add, Aq, (T*)F.partial, e0, estride);
     __threadfence_system();
-    __syncwarp();
-    unsigned ticket = 0;
-    if (lane == 0) ticket = atomicAdd(H.ticket, 1u);
-    ticket = __shfl_sync(0xffffffffu, ticket, 0);
-    if (ticket == gridDim.x - 1) {  // every CTA's rows are out: raise the epoch flag at every peer
-      __threadfence_system();
-      for (int p = lane; p < H.nPeers; p += 32) {
-        volatile unsigned long long* f = H.peerFlags[p] + H.myRank;
-        *f = H.epoch;
-      }
-      if (lane == 0) *H.ticket = 0u;
+    __syncthreads();
+    // this pusher's rows are out: raise ITS flag slot at every peer (receivers wait for all kFlagSlots slots)
+    for (int p = tid; p < H.nPeers; p += blockDim.x) {
+      volatile unsigned long long* f = H.peerFlags[p] + (size_t)H.myRank * kFlagSlots + pb;
+      *f = H.epoch;
     }
     return;
   }
@@ -176,7 +187,7 @@ __global__ void __launch_bounds__(NGROUPS* Nq* Nq + (kFused ? 64 : 32), 1)
       for (int i = 0; i < myCount; ++i) {
         const int s = i % NSTAGES;
         if (i >= NSTAGES) mbar_wait(&empty[s], ((i / NSTAGES) - 1) & 1);
-        const dlong element = elementList[blockIdx.x + (dlong)i * gridDim.x];
+        const dlong element = elementList[blockIdx.x + (dlong)i * nAx];
         T* st = stages + (size_t)s * stageElems;
         mbar_expect_tx(&full[s], gBytes + qBytes);
         bulk_g2s_hint(st, ggeo + (size_t)element * 7 * Np, gBytes, &full[s], pol);
@@ -200,7 +211,7 @@ __global__ void __launch_bounds__(NGROUPS* Nq* Nq + (kFused ? 64 : 32), 1)
 
   for (int i = g; i < myCount; i += NGROUPS) {
     const int s = i % NSTAGES;
-    const dlong element = elementList[blockIdx.x + (dlong)i * gridDim.x];
+    const dlong element = elementList[blockIdx.x + (dlong)i * nAx];
     const T* st = stages + (size_t)s * stageElems;
     const T* sq = st + NG * Np;
     mbar_wait(&full[s], (i / NSTAGES) & 1);
@@ -313,7 +324,7 @@ __global__ void __launch_bounds__(NGROUPS* Nq* Nq + (kFused ? 64 : 32), 1)
       if constexpr (!kPoisson) v += r_mass[k];
       Ae[k * Nq2] = v;
     }
-    const bool haloElem = kFused && (blockIdx.x + (dlong)i * gridDim.x < F.NhaloElements);
+    const bool haloElem = kFused && (blockIdx.x + (dlong)i * nAx < F.NhaloElements);
     if (haloElem) __threadfence();
     group_sync(1 + g, Nq2);  // su/ss are rewritten by the next element of this group
     if (haloElem && t == 0) atomicAdd(F.counter, 1ull);
@@ -340,7 +351,8 @@ static int launch_tma(dlong Nelements, const dlong* elementList, const T* ggeo, 
   int grid = kNumSMs;
   if (grid > Nelements) grid = Nelements;
   const FusedHalo F = fused ? *fused : FusedHalo();
-  kern<<<grid, NGROUPS * Nq * Nq + (kFused ? 64 : 32), smem, stream>>>(Nelements, elementList, ggeo, Dm, lambda0,
+  if (kFused) grid = kNumSMs;  // pushers + workers, all co-resident
+  kern<<<grid, NGROUPS * Nq * Nq + 32, smem, stream>>>(Nelements, elementList, ggeo, Dm, lambda0,
                                                                         lambda1, q, Aq, F);
   NRSB_CHECK_LAUNCH();
   return NRSB_OK;

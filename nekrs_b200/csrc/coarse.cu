@@ -414,7 +414,7 @@ int coarseSolver_t::solve(float* rhs, float* xE)
   const int grid = (NT + kBlockSize - 1) / kBlockSize;
   double* S = scal.p;
   int rc;
-  if (variant == 1 && clusterSize > 0 && (!multiRank || replicated)) return solve_cluster(rhs, xE);
+  if (variant >= 1 && clusterSize > 0 && (!multiRank || replicated)) return solve_cluster(rhs, xE);
   iterOnDevice = false;
   lastIter = 0;
   if (NT > 0) {

@@ -342,7 +342,7 @@ int coarseSolver_t::plan_cluster()
     const int tryU[3] = {0, 0, 1}, tryM[3] = {1, 0, 0};
     int pick = -1;
     size_t smem = 0;
-    for (int o = 0; o < 3 && pick < 0; ++o) {
+    for (int o = (variant == 2 ? 2 : 0); o < 3 && pick < 0; ++o) {  // variant 2 (tests): force the L2 path
       smem = fixed + (tryU[o] ? 0 : uBytes) + (tryM[o] ? mat : 0);
       if (smem <= limit) pick = o;
     }

@@ -15,6 +15,8 @@
 //  * mask + on-rank gather-scatter + halo unpack are a single kernel after Ax.
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "host.hpp"
@@ -182,11 +184,42 @@ int ellipticOperator(elliptic_t* elliptic, const T* o_q, T* o_Aq, bool masked)
     // belong to no row of the masked handle, so it commutes with every sum).
     FusedHalo F;
     if ((rc = oogs->begin_fused(&F, mesh->NglobalGatherElements, elliptic->fieldOffset))) return rc;
+    // developer aid (NRSB_OP_TIMING=1): per-kernel times of the pipelined operator, no host sync per step
+    static const bool timing = getenv("NRSB_OP_TIMING") != nullptr;
+    static std::vector<cudaEvent_t> ev;
+    static int nrec = 0;
+    constexpr int kRing = 50;
+    if (timing) {
+      if (ev.empty()) {
+        ev.resize(3 * kRing);
+        for (auto& x : ev) cudaEventCreate(&x);
+      }
+      cudaEventRecord(ev[3 * nrec], elliptic->stream);
+    }
     if ((rc = ax_tma_fused_launch<T>(mesh->Nq, 5, mesh->Nelements, mesh->o_haloFirstElementList.p, P::ggeo(mesh),
                                      P::D(mesh), P::lambda0(elliptic), P::lambda1(elliptic), elliptic->poisson ? 1 : 0,
                                      o_q, o_Aq, F, elliptic->stream)))
       return rc;
-    return oogs->finish<T>(o_Aq, 1, elliptic->fieldOffset, gs_op::add, nm, elliptic->o_maskIds.p, elliptic->stream);
+    if (timing) cudaEventRecord(ev[3 * nrec + 1], elliptic->stream);
+    rc = oogs->finish<T>(o_Aq, 1, elliptic->fieldOffset, gs_op::add, nm, elliptic->o_maskIds.p, elliptic->stream);
+    if (timing) {
+      cudaEventRecord(ev[3 * nrec + 2], elliptic->stream);
+      if (++nrec == kRing) {
+        cudaEventSynchronize(ev[3 * kRing - 1]);
+        double sa = 0, sb = 0;
+        for (int i = 0; i < kRing; ++i) {
+          float x = 0, y = 0;
+          cudaEventElapsedTime(&x, ev[3 * i], ev[3 * i + 1]);
+          cudaEventElapsedTime(&y, ev[3 * i + 1], ev[3 * i + 2]);
+          sa += x;
+          sb += y;
+        }
+        fprintf(stderr, "[rank %d] fused operator: Ax+push %.2f us, finish %.2f us (mean of %d, pipelined)\n",
+                mesh->comm ? mesh->comm->rank : 0, sa / kRing * 1e3, sb / kRing * 1e3, kRing);
+        nrec = 0;
+      }
+    }
+    return rc;
   }
   if (elliptic->overlap) {
     if ((rc = ellipticAx<T>(elliptic, mesh->NglobalGatherElements, mesh->o_globalGatherElementList.p, o_q, o_Aq)))

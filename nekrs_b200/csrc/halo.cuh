@@ -6,6 +6,9 @@
 
 namespace nrsb {
 
+constexpr int kFlagSlots = 8;    // arrival flags per sender: one per pusher CTA of the fused launch
+constexpr int kInlinePeers = 8;  // peer window pointers carried in the kernel parameters (no dependent load)
+
 struct HaloExchangeDev {
   int nRows;
   const int* rowStarts;  // local copies CSR
@@ -13,6 +16,17 @@ struct HaloExchangeDev {
   const int* sendStarts;  // per row: destinations
   const int* sendPeer;    // peer index
   const int* sendSlot;    // slot inside my block of that peer's window
+  // flat send table for one field (k = 1): one entry per (row, destination), sorted by row.
+  //   sendFlat[e] = {id0, id1 (-1: single local copy), peer | kSendFirst | kSendSlow, absolute slot in the peer window}
+  //   (kSendSlow: more than two local copies, id0 = row index -> CSR walk);  sendRow[e] = row
+  int nSend;
+  const int4* sendFlat;
+  const int* sendRow;
+  // flat receive table for one field: recvFlat[row] = {absolute slot a, absolute slot b, position of the own
+  // partial among the contributions (ascending rank), number of contributions}; valid when that number <= 3,
+  // else -1 in .w -> CSR walk.  rowLocal[row] = {id0, id1 (-1), number of local copies, 0}
+  const int4* recvFlat;
+  const int4* rowLocal;
   const int* recvStarts;  // per row: contributions in ascending rank order
   const int* recvPeer;    // peer index or -1 for the own partial
   const int* recvSlot;
@@ -22,6 +36,7 @@ struct HaloExchangeDev {
   const int* peerCount;          // shared rows with peer
   const int* peerRank;
   void* const* peerWindow;  // this parity
+  void* peerWindowInline[kInlinePeers];
   void* myWindow;           // this parity
   unsigned long long* const* peerFlags;
   unsigned long long* myFlags;
@@ -59,9 +74,78 @@ __device__ __forceinline__ void halo_pack_row(const HaloExchangeDev& H, const in
   }
 }
 
+constexpr int kSendFirst = 1 << 16;  // first destination of its row: also stores partial[row]
+constexpr int kSendSlow = 1 << 17;
+
+// kB send entries per thread in two steps, so that a caller can issue the index loads BEFORE the data is
+// ready (they do not depend on it) and keep only  value load -> NVLink store  on the critical path.
+template <int kB>
+struct HaloSendBatch {
+  int4 s[kB];
+  int row[kB];
+};
+
+template <int kB>
+__device__ __forceinline__ void halo_pack_load(const HaloExchangeDev& H, const int e0, const int estride,
+                                               HaloSendBatch<kB>& b)
+{
+#pragma unroll
+  for (int j = 0; j < kB; ++j) {
+    const int e = e0 + j * estride;
+    b.s[j] = make_int4(-1, -1, 0, 0);
+    b.row[j] = 0;
+    if (e < H.nSend) {
+      b.s[j] = H.sendFlat[e];
+      b.row[j] = H.sendRow[e];
+    }
+  }
+}
+
+template <typename T, int kB, bool kL2>
+__device__ __forceinline__ void halo_pack_store(const HaloExchangeDev& H, const gs_op op, const T* __restrict__ v,
+                                                T* __restrict__ partial, const int e0, const int estride,
+                                                const HaloSendBatch<kB>& b)
+{
+  T val[kB];
+  auto ld = [&](int id) -> T { return kL2 ? __ldcg(v + id) : v[id]; };
+#pragma unroll
+  for (int j = 0; j < kB; ++j) {
+    val[j] = T(0);
+    if (e0 + j * estride < H.nSend) {
+      if (b.s[j].z & kSendSlow) {
+        const int s0 = H.rowStarts[b.row[j]], s1 = H.rowStarts[b.row[j] + 1];
+        T a = ld(H.rowIds[s0]);
+        for (int c = s0 + 1; c < s1; ++c) a = gs_combine(a, ld(H.rowIds[c]), op);
+        val[j] = a;
+      } else {
+        const T a = ld(b.s[j].x);
+        val[j] = (b.s[j].y >= 0) ? gs_combine(a, ld(b.s[j].y), op) : a;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kB; ++j)
+    if (e0 + j * estride < H.nSend) {
+      if (b.s[j].z & kSendFirst) partial[b.row[j]] = val[j];
+      const int p = b.s[j].z & 0xffff;
+      T* w = (T*)(p < kInlinePeers ? H.peerWindowInline[p] : H.peerWindow[p]);
+      w[b.s[j].w] = val[j];  // NVLink store
+    }
+}
+
+template <typename T, int kB, bool kL2>
+__device__ __forceinline__ void halo_pack_flat(const HaloExchangeDev& H, const gs_op op, const T* __restrict__ v,
+                                               T* __restrict__ partial, const int e0, const int estride)
+{
+  HaloSendBatch<kB> b;
+  halo_pack_load<kB>(H, e0, estride, b);
+  halo_pack_store<T, kB, kL2>(H, op, v, partial, e0, estride, b);
+}
+
 // what the fused axhelm kernel needs besides the exchange itself
 struct FusedHalo {
   HaloExchangeDev H;
+  int nPush = kFlagSlots;              // CTAs of the launch that only push halo sums (no element work)
   dlong NhaloElements = 0;             // the first NhaloElements entries of the element list touch halo rows
   unsigned long long* counter = nullptr;  // monotonically increasing count of finished halo elements
   unsigned long long target = 0;          // value of *counter once this launch's halo elements are all stored

@@ -72,6 +72,7 @@ template struct dbuf<unsigned>;
 template struct dbuf<unsigned long long>;
 template struct dbuf<double*>;
 template struct dbuf<float*>;
+template struct dbuf<int4>;
 template struct dbuf<unsigned long long*>;
 template struct dbuf<void*>;
 template struct dbuf<long>;

@@ -33,7 +33,11 @@ __global__ void __launch_bounds__(kBlockSize)
                      T* __restrict__ partial)
 {
   const long gid = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid < (long)H.nRows * k) halo_pack_row<T>(H, k, stride, op, v, partial, (int)(gid % H.nRows), (int)(gid / H.nRows));
+  if (k == 1) {
+    halo_pack_flat<T, 1, false>(H, op, v, partial, (int)gid, 0);
+  } else if (gid < (long)H.nRows * k) {
+    halo_pack_row<T>(H, k, stride, op, v, partial, (int)(gid % H.nRows), (int)(gid / H.nRows));
+  }
   // publish: every block fences its remote stores, the last one raises the flags
   __shared__ bool last;
   __threadfence_system();
@@ -45,8 +49,8 @@ __global__ void __launch_bounds__(kBlockSize)
   __syncthreads();
   if (last) {
     __threadfence_system();
-    for (int p = threadIdx.x; p < H.nPeers; p += blockDim.x) {
-      volatile unsigned long long* f = H.peerFlags[p] + H.myRank;
+    for (int p = threadIdx.x; p < H.nPeers * kFlagSlots; p += blockDim.x) {
+      volatile unsigned long long* f = H.peerFlags[p / kFlagSlots] + (size_t)H.myRank * kFlagSlots + p % kFlagSlots;
       *f = H.epoch;
     }
     if (threadIdx.x == 0) *H.ticket = 0u;
@@ -115,8 +119,9 @@ __device__ __forceinline__ void unpack_rows_body(const HaloExchangeDev& H, const
   }
   // ---- halo rows: wait for every peer's epoch flag, then fold
   if (blockIdx.y != 0) return;  // halo blocks handle all fields themselves
-  if (threadIdx.x < H.nPeers) {
-    volatile unsigned long long* f = H.myFlags + H.peerRank[threadIdx.x];
+  if (threadIdx.x < H.nPeers * kFlagSlots) {
+    volatile unsigned long long* f =
+        H.myFlags + (size_t)H.peerRank[threadIdx.x / kFlagSlots] * kFlagSlots + threadIdx.x % kFlagSlots;
     while (*f < H.epoch) {
     }
   }
@@ -127,6 +132,28 @@ __device__ __forceinline__ void unpack_rows_body(const HaloExchangeDev& H, const
   const int row = gid % H.nRows;
   const int f = gid / H.nRows;
   const volatile T* w = (const volatile T*)H.myWindow;
+  if (k == 1) {
+    // common case through the flat tables: two independent index loads, then the values, then the stores
+    const int4 rf = H.recvFlat[row];
+    const int4 rl = H.rowLocal[row];
+    if (rf.w > 0 && rl.z <= 2) {
+      const T own = partial[row];
+      const T a = w[rf.x];
+      const T b = (rf.w == 3) ? w[rf.y] : T(0);
+      T tot;
+      if (rf.w == 2) {
+        tot = (rf.z == 0) ? gs_combine(own, a, op) : gs_combine(a, own, op);
+      } else {  // three contributions, own partial at position rf.z, the two remote ones in ascending rank order
+        const T c0 = (rf.z == 0) ? own : a;
+        const T c1 = (rf.z == 0) ? a : (rf.z == 1 ? own : b);
+        const T c2 = (rf.z == 2) ? own : b;
+        tot = gs_combine(gs_combine(c0, c1, op), c2, op);
+      }
+      v[rl.x] = tot;
+      if (rl.y >= 0) v[rl.y] = tot;
+      return;
+    }
+  }
   T tot = T(0);
   bool first = true;
   for (int c = H.recvStarts[row]; c < H.recvStarts[row + 1]; ++c) {
@@ -158,6 +185,9 @@ __global__ void __launch_bounds__(kBlockSize)
 
 // ------------------------------------------------------------------------------------------
 struct oogs_dev_t {
+  std::vector<void*> h_peerWindow[2];
+  dbuf<int4> sendFlat, recvFlat, rowLocal;
+  dbuf<int> sendRow;
   dbuf<long> peerRemoteOffset, peerRecvOffset;
   dbuf<int> peerCount, peerRank;
   dbuf<int> recvPeer, recvSlot;
@@ -239,7 +269,7 @@ int oogs_t::setup(ogs_t* ogs_, comm_t* comm_, int maxFields_)
   auto dev = std::make_unique<oogs_dev_t>();
   // arena = [window parity 0][window parity 1][flags nranks]
   dev->windowBytes = ((windowSlots * maxFields * sizeof(double) + 255) / 256) * 256;
-  const size_t arenaBytes = 2 * dev->windowBytes + sizeof(unsigned long long) * nranks;
+  const size_t arenaBytes = 2 * dev->windowBytes + sizeof(unsigned long long) * nranks * kFlagSlots;
   NRSB_CUDA(cudaMalloc(&dev->arena, arenaBytes));
   NRSB_CUDA(cudaMemset(dev->arena, 0, arenaBytes));
   NRSB_CUDA(cudaDeviceSynchronize());
@@ -271,6 +301,8 @@ int oogs_t::setup(ogs_t* ogs_, comm_t* comm_, int maxFields_)
   if ((rc = dev->peerRecvOffset.upload(recOff))) return rc;
   if ((rc = dev->peerCount.upload(cnt))) return rc;
   if ((rc = dev->peerRank.upload(prank))) return rc;
+  dev->h_peerWindow[0] = win[0];
+  dev->h_peerWindow[1] = win[1];
   if ((rc = dev->d_peerWindow[0].upload(win[0]))) return rc;
   if ((rc = dev->d_peerWindow[1].upload(win[1]))) return rc;
   if ((rc = d_peerFlags.upload(pflags))) return rc;
@@ -298,6 +330,47 @@ int oogs_t::setup(ogs_t* ogs_, comm_t* comm_, int maxFields_)
     }
     sendStarts[r + 1] = (int)sendPeer.size();
     recvStarts[r + 1] = (int)recvPeer.size();
+  }
+  {
+    std::vector<int4> flat(sendPeer.size());
+    std::vector<int> frow(sendPeer.size());
+    for (int r = 0; r < nRows; ++r) {
+      const int c0 = ogs->haloGatherOffsets[r], c1 = ogs->haloGatherOffsets[r + 1];
+      for (int d = sendStarts[r]; d < sendStarts[r + 1]; ++d) {
+        int code = sendPeer[d];
+        if (d == sendStarts[r]) code |= kSendFirst;
+        int id0 = ogs->haloGatherIds[c0], id1 = -1;
+        if (c1 - c0 == 2) id1 = ogs->haloGatherIds[c0 + 1];
+        if (c1 - c0 > 2) {
+          code |= kSendSlow;
+          id0 = r;
+        }
+        flat[d] = make_int4(id0, id1, code, (int)(peers[sendPeer[d]].remoteOffset + sendSlot[d]));
+        frow[d] = r;
+      }
+    }
+    if ((rc = dev->sendFlat.upload(flat))) return rc;
+    if ((rc = dev->sendRow.upload(frow))) return rc;
+    std::vector<int4> rflat(nRows), rloc(nRows);
+    for (int r = 0; r < nRows; ++r) {
+      const int c0 = ogs->haloGatherOffsets[r], c1 = ogs->haloGatherOffsets[r + 1];
+      rloc[r] = make_int4(ogs->haloGatherIds[c0], c1 - c0 >= 2 ? ogs->haloGatherIds[c0 + 1] : -1, c1 - c0, 0);
+      const int n = recvStarts[r + 1] - recvStarts[r];
+      int4 e = make_int4(0, 0, 0, -1);
+      if (n == 2 || n == 3) {
+        int slots[2] = {0, 0}, ns = 0, ownPos = 0;
+        for (int c = recvStarts[r]; c < recvStarts[r + 1]; ++c) {
+          if (recvPeer[c] < 0)
+            ownPos = c - recvStarts[r];
+          else
+            slots[ns++] = (int)(peers[recvPeer[c]].recvOffset + recvSlot[c]);
+        }
+        e = make_int4(slots[0], slots[1], ownPos, n);
+      }
+      rflat[r] = e;
+    }
+    if ((rc = dev->recvFlat.upload(rflat))) return rc;
+    if ((rc = dev->rowLocal.upload(rloc))) return rc;
   }
   if ((rc = d_sendStarts.upload(sendStarts))) return rc;
   if ((rc = d_sendPeer.upload(sendPeer))) return rc;
@@ -333,6 +406,11 @@ static HaloExchangeDev make_dev(oogs_t* o, oogs_dev_t* d, int parity)
   H.sendStarts = o->d_sendStarts.p;
   H.sendPeer = o->d_sendPeer.p;
   H.sendSlot = o->d_sendSlot.p;
+  H.nSend = (int)d->sendFlat.n;
+  H.sendFlat = d->sendFlat.p;
+  H.sendRow = d->sendRow.p;
+  H.recvFlat = d->recvFlat.p;
+  H.rowLocal = d->rowLocal.p;
   H.recvStarts = o->d_recvStarts.p;
   H.recvPeer = d->recvPeer.p;
   H.recvSlot = d->recvSlot.p;
@@ -342,6 +420,8 @@ static HaloExchangeDev make_dev(oogs_t* o, oogs_dev_t* d, int parity)
   H.peerCount = d->peerCount.p;
   H.peerRank = d->peerRank.p;
   H.peerWindow = d->d_peerWindow[parity].p;
+  for (int p = 0; p < kInlinePeers; ++p)
+    H.peerWindowInline[p] = p < (int)d->h_peerWindow[parity].size() ? d->h_peerWindow[parity][p] : nullptr;
   H.myWindow = (char*)d->arena + (size_t)parity * d->windowBytes;
   H.peerFlags = o->d_peerFlags.p;
   H.myFlags = (unsigned long long*)((char*)d->arena + 2 * d->windowBytes);
@@ -356,11 +436,11 @@ int oogs_t::start(T* v, int k, dlong stride, gs_op op, cudaStream_t stream)
 {
   if (!ogs || ogs->NhaloGather == 0) return NRSB_OK;
   NRSB_REQUIRE(k <= maxFields, "oogs::start: more fields than the handle was set up for");
-  NRSB_REQUIRE((int)peers.size() <= kBlockSize, "too many neighbour ranks");
+  NRSB_REQUIRE((int)peers.size() * kFlagSlots <= kBlockSize, "too many neighbour ranks");
   oogs_dev_t* d = g_dev[this].get();
   ++epoch;
   HaloExchangeDev H = make_dev(this, d, (int)(epoch & 1ull));
-  const long total = (long)H.nRows * k;
+  const long total = (k == 1) ? (long)H.nSend : (long)H.nRows * k;
   halo_pack_kernel<T><<<(unsigned)((total + kBlockSize - 1) / kBlockSize), kBlockSize, 0, stream>>>(
       H, k, stride, op, v, (T*)d_partial.p);
   NRSB_CHECK_LAUNCH();

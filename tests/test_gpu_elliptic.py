@@ -253,6 +253,11 @@ def test_coarse_cluster_kernel_matches_multilaunch_and_oracle(orc, nel):
     import ctypes
     from nekrs_b200 import lib as _lib
     mesh, opts, ell, ref = _mg_case(orc, 3, nel, "FOURTHOPTCHEBYSHEV+RAS")
+    _lib.call("nrsb_set_coarse_variant", ctypes.c_int(2))   # plan made at setup: SpMV input through L2
+    try:
+        ell_l2 = Elliptic(mesh, opts)
+    finally:
+        _lib.call("nrsb_set_coarse_variant", ctypes.c_int(1))
     k = ell.get_int("nLevels") - 1
     n1 = ell.get_int("level%d:Nlocal" % k)
     rhs = np.random.Generator(np.random.PCG64(3)).random(n1).astype(np.float32) - 0.5
@@ -269,7 +274,35 @@ def test_coarse_cluster_kernel_matches_multilaunch_and_oracle(orc, nel):
         _lib.call("nrsb_set_coarse_variant", ctypes.c_int(1))
     assert out[1][1] == out[0][1] and out[1][1] > 0
     assert relerr(out[1][0], out[0][0]) < 2e-5
+    d_x = DB.zeros(n1, np.float32)
+    ell_l2.level_op(k, "coarseSolve", DB(like=rhs), d_x)
+    assert ell_l2.get_int("coarseIterations") == out[1][1]
+    assert np.array_equal(d_x.download(), out[1][0])        # same arithmetic, different staging of u
     x_ref = np.zeros(n1, np.float32)
     ref.coarse.solve(rhs, x_ref)
     assert abs(out[1][1] - ref.coarse.last_iter) <= 8
     assert relerr(out[1][0], x_ref) < 2e-3
+
+
+def test_coarse_cluster_kernel_large_grid():
+    """68 921 coarse unknowns: 8 rows per thread, SpMV input through L2 (what the replicated coarse problem
+    of an 8-GPU job looks like).  Product-only check: cluster kernel == multi-launch path."""
+    import ctypes
+    from nekrs_b200 import lib as _lib
+    mesh = meshgen.box_mesh(3, (42, 42, 42), kershaw_eps=0.3)
+    opts = pressure_options(**{"MULTIGRID SMOOTHER": "FOURTHOPTCHEBYSHEV+RAS"})
+    ell = Elliptic(mesh, opts)
+    k = ell.get_int("nLevels") - 1
+    n1 = ell.get_int("level%d:Nlocal" % k)
+    rhs = np.random.Generator(np.random.PCG64(3)).random(n1).astype(np.float32) - 0.5
+    out = {}
+    try:
+        for variant in (1, 0):
+            _lib.call("nrsb_set_coarse_variant", ctypes.c_int(variant))
+            d_x = DB.zeros(n1, np.float32)
+            ell.level_op(k, "coarseSolve", DB(like=rhs), d_x)
+            out[variant] = (d_x.download(), ell.get_int("coarseIterations"))
+    finally:
+        _lib.call("nrsb_set_coarse_variant", ctypes.c_int(1))
+    assert out[1][1] == out[0][1] and out[1][1] > 0
+    assert relerr(out[1][0], out[0][0]) < 5e-5
