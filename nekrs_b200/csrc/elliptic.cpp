@@ -26,7 +26,8 @@
 namespace nrsb {
 
 // device scalar slots
-enum { S_RDOTZ = 0, S_RDOTZ_OLD, S_PAP, S_RDOTR, S_ZDOTAP, S_ALPHA, S_BETA, S_SUM, S_NORM, S_GMRES = 16, S_COUNT = 64 };
+enum { S_RDOTZ = 0, S_RDOTZ_OLD, S_PAP, S_RDOTR, S_ZDOTAP, S_ALPHA, S_BETA, S_SUM, S_NORM, S_DONE, S_ITERDONE, S_CURNORM,
+       S_GMRES = 16, S_COUNT = 64 };
 
 elliptic_t::elliptic_t() {}
 elliptic_t::~elliptic_t()
@@ -482,7 +483,29 @@ int pcg(elliptic_t* elliptic, double* o_r, double* o_x, double tol, int MAXIT, d
   NRSB_CUDA(cudaMemcpyAsync(S + S_RDOTR, &h_rdotr, sizeof(double), cudaMemcpyHostToDevice, st));
   NRSB_CUDA(cudaStreamSynchronize(st));
 
+  // The loop runs ahead of the host: the residual norm, its history and the convergence flag live on the
+  // device (PcgControl); the host looks at the flag every `interval` iterations only.  Once the flag is up,
+  // x and r are frozen, so the solution and the iteration count are exactly those of the reference's
+  // check-every-iteration loop (PCG.cpp:115-200); the iterations launched in between are wasted work,
+  // which is why the interval is 1 when an iteration is expensive (multigrid).
+  int interval = options.compareArgs("PRECONDITIONER", "MULTIGRID") ? 1 : 8;
+  options.getArgs("PCG CHECK INTERVAL", interval);
+  interval = std::max(1, interval);
+  if (elliptic->o_resHist.n < (size_t)MAXIT + 1)
+    if ((rc = elliptic->o_resHist.alloc((size_t)MAXIT + 1))) return rc;
+  {
+    const double init[3] = {0.0, 0.0, rdotr};
+    NRSB_CUDA(cudaMemcpyAsync(S + S_DONE, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    NRSB_CUDA(cudaStreamSynchronize(st));
+  }
+  PcgControl ctl;
+  ctl.ctl = S + S_DONE;
+  ctl.hist = elliptic->o_resHist.p;
+  ctl.factor = elliptic->resNormFactor;
+  ctl.tol = tol;
+
   int iter = 0;
+  bool done = false;
   do {
     iter++;
     // rdotz2 = rdotz1
@@ -491,7 +514,9 @@ int pcg(elliptic_t* elliptic, double* o_r, double* o_x, double tol, int MAXIT, d
       if ((rc = ellipticPreconditioner(elliptic, o_r, o_z))) return rc;
       if ((rc = wdot_launch<double>(N, o_weight, o_r, o_z, S + S_RDOTZ, elliptic->ws, st))) return rc;
     } else {
-      NRSB_CUDA(cudaMemcpyAsync(S + S_RDOTZ, S + S_RDOTR, sizeof(double), cudaMemcpyDeviceToDevice, st));
+      // rdotz1 = rdotr: the residual NORM of the previous iteration (device copy kept by PcgCtlPost)
+      NRSB_CUDA(cudaMemcpyAsync(S + S_RDOTZ, iter == 1 ? S + S_RDOTR : S + S_CURNORM, sizeof(double),
+                                cudaMemcpyDeviceToDevice, st));
     }
     DevScalar beta = DevScalar::host(0.0);
     if (iter > 1) {
@@ -508,23 +533,34 @@ int pcg(elliptic_t* elliptic, double* o_r, double* o_x, double tol, int MAXIT, d
     // p = z + beta p
     if ((rc = axpby_launch<double>(N, DevScalar::host(1.0), o_z, beta, o_p, st))) return rc;
     if ((rc = ellipticOperator<double>(elliptic, o_p, o_Ap))) return rc;
-    if ((rc = wdot_launch<double>(N, o_weight, o_p, o_Ap, S + S_PAP, elliptic->ws, st))) return rc;
-    // alpha = rdotz1 / (pAp + 1e-300)
-    if ((rc = set_scalar_launch(S + S_ALPHA, DevScalar::ratio(S + S_RDOTZ, S + S_PAP, 1.0, 1e-300), st))) return rc;
+    // pAp and alpha = rdotz1 / (pAp + 1e-300) in one launch
+    if ((rc = wdot_ratio_launch(N, o_weight, o_p, o_Ap, S + S_PAP, S + S_RDOTZ, 1e-300, S + S_ALPHA, elliptic->ws, st)))
+      return rc;
     DevScalar alpha = DevScalar::ratio(S + S_ALPHA, nullptr);
-    // x += alpha p ; r -= alpha Ap ; rdotr = sum w r^2      (one kernel)
-    if ((rc = update_pcg_launch(N, o_weight, o_Ap, o_p, alpha, o_r, o_x, S + S_NORM, elliptic->ws, st))) return rc;
-    double v;
-    if ((rc = elliptic->read_scalars(S_NORM, 1, &v))) return rc;
-    rdotr = std::sqrt(v * elliptic->resNormFactor);
-    h_rdotr = rdotr;
-    NRSB_CUDA(cudaMemcpyAsync(S + S_RDOTR, &h_rdotr, sizeof(double), cudaMemcpyHostToDevice, st));
-    elliptic->resHistory.push_back(rdotr);
-    if (std::isnan(rdotr)) {
-      set_last_error("Detected invalid resiual norm while running linear solver!");
-      return NRSB_ERR_DIVERGED;
+    // x += alpha p ; r -= alpha Ap ; rdotr = sqrt(sum w r^2 * factor) ; history ; convergence flag  (one kernel)
+    ctl.iter = iter;
+    if ((rc = update_pcg_ctl_launch(N, o_weight, o_Ap, o_p, alpha, o_r, o_x, S + S_NORM, ctl, elliptic->ws, st)))
+      return rc;
+    if (iter % interval == 0 || iter == MAXIT) {
+      double v[2];
+      if ((rc = elliptic->read_scalars(S_DONE, 2, v))) return rc;
+      if (v[0] != 0.0) {
+        done = true;
+        iter = (int)v[1];
+      }
     }
-  } while (rdotr > tol && iter < MAXIT);
+  } while (!done && iter < MAXIT);
+  {
+    std::vector<double> h(iter);
+    NRSB_CUDA(cudaMemcpyAsync(h.data(), elliptic->o_resHist.p, sizeof(double) * iter, cudaMemcpyDeviceToHost, st));
+    NRSB_CUDA(cudaStreamSynchronize(st));
+    for (double v : h) elliptic->resHistory.push_back(v);
+    if (iter > 0) rdotr = h[iter - 1];
+  }
+  if (std::isnan(rdotr)) {
+    set_last_error("Detected invalid resiual norm while running linear solver!");
+    return NRSB_ERR_DIVERGED;
+  }
   elliptic->Niter = iter;
   return NRSB_OK;
 }

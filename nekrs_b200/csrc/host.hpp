@@ -310,6 +310,7 @@ class elliptic_t {
   std::unique_ptr<ogs_t> ogs;
   std::unique_ptr<oogs_t> oogs;
   bool overlap = false;  // oogsAx != oogs in the reference: split Ax into halo / interior elements
+  dbuf<double> o_resHist;  // device-side residual history of the current PCG solve
   bool fusedHaloAx = true;  // overlap through ONE launch (axhelm + in-kernel halo push) when Nq == 8
   dlong Nmasked = 0, NmaskedLocal = 0, NmaskedGlobal = 0;
   dbuf<dlong> o_maskIds, o_maskIdsLocal, o_maskIdsGlobal;

@@ -249,6 +249,52 @@ int update_pcg_launch(long N, const double* w, const double* Ap, const double* p
   return reduce_launch<1>(N, op, 1, out, ws, s);
 }
 
+namespace {
+struct PcgCtlPost {
+  PcgControl c;
+  __device__ __forceinline__ void operator()(double* tot) const
+  {
+    if (c.ctl[0] != 0.0) return;  // frozen
+    const double rd = sqrt(tot[0] * c.factor);
+    c.ctl[2] = rd;
+    c.hist[c.iter - 1] = rd;
+    if (!(rd > c.tol)) {  // also taken for NaN, like the reference's loop condition
+      c.ctl[0] = 1.0;
+      c.ctl[1] = (double)c.iter;
+    }
+  }
+};
+struct RatioPost {
+  const double* num;
+  double shift;
+  double* alpha;
+  __device__ __forceinline__ void operator()(double* tot) const { alpha[0] = num[0] / (tot[0] + shift); }
+};
+}  // namespace
+
+int update_pcg_ctl_launch(long N, const double* w, const double* Ap, const double* p, DevScalar alpha, double* r,
+                          double* x, double* out, PcgControl c, const ReduceWs& ws, cudaStream_t s)
+{
+  const double* done = c.ctl;
+  auto op = [=] __device__(long i, double* acc) {
+    if (__ldg(done) != 0.0) return;
+    const double a = alpha.eval();
+    const double rn = r[i] - a * Ap[i];
+    r[i] = rn;
+    x[i] = a * p[i] + x[i];
+    acc[0] += rn * rn * w[i];
+  };
+  return reduce_launch<1>(N, op, 1, out, ws, s, PcgCtlPost{c});
+}
+
+int wdot_ratio_launch(long N, const double* w, const double* x, const double* y, double* out, const double* num,
+                      double shift, double* alpha, const ReduceWs& ws, cudaStream_t s)
+{
+  return reduce_launch<1>(
+      N, [=] __device__(long i, double* acc) { acc[0] += x[i] * y[i] * w[i]; }, 1, out, ws, s,
+      RatioPost{num, shift, alpha});
+}
+
 int gram_schmidt_launch(long N, long offset, int gmresSize, const double* w, const double* y, const double* V,
                         double* wv, double* out, const ReduceWs& ws, cudaStream_t s)
 {

@@ -95,6 +95,22 @@ int wdot_multi_launch(long N, int NVec, long offset, const double* w, const doub
 int update_pcg_launch(long N, const double* w, const double* Ap, const double* p, DevScalar alpha, double* r,
                       double* x, double* out, const ReduceWs& ws, cudaStream_t s);
 
+// Device-resident PCG control: the same update, but the post step of the reduction turns the sum into the
+// residual norm, appends it to a device history, and raises `ctl[0]` once it is <= tol; a raised flag
+// freezes x and r in every later launch (iterations launched ahead of the host's convergence check become
+// no-ops on the solution).  ctl = {done, iteration at which done was raised, current norm}.
+struct PcgControl {
+  double* ctl = nullptr;
+  double* hist = nullptr;
+  double factor = 1.0, tol = 0.0;
+  int iter = 0;
+};
+int update_pcg_ctl_launch(long N, const double* w, const double* Ap, const double* p, DevScalar alpha, double* r,
+                          double* x, double* out, PcgControl c, const ReduceWs& ws, cudaStream_t s);
+// out = sum w x y ; alpha[0] = num[0] / (out + shift)   (pAp and the step length in one launch)
+int wdot_ratio_launch(long N, const double* w, const double* x, const double* y, double* out, const double* num,
+                      double shift, double* alpha, const ReduceWs& ws, cudaStream_t s);
+
 // Chebyshev updates (updateChebyshev.okl, updateFourthKindChebyshev.okl)
 int update_chebyshev_launch(long N, float dCoeff, float rCoeff, const float* SAd, float* d, float* r, float* x,
                             cudaStream_t s);
