@@ -240,14 +240,19 @@ def run_ours(args):
     for _ in range(min(args.steps, 20)):
         e2e_ms.append(bench.e2e_step())
     barrier()
+    # the queued host entry: same bytes per step, copies of neighbouring steps overlap (both copy engines)
+    bench.e2e_pipelined(4)
+    barrier()
+    e2e_pipe_ms = bench.e2e_pipelined(min(args.steps, 20))
+    barrier()
     clocks = sampler.stop() if sampler else None
     e2e_ms_mean = float(np.mean(e2e_ms))
 
     if dist is not None:
         import torch
-        t = torch.tensor([ms_per_step, ms_ax, e2e_ms_mean], device="cuda", dtype=torch.float64)
+        t = torch.tensor([ms_per_step, ms_ax, e2e_ms_mean, e2e_pipe_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_per_step, ms_ax, e2e_ms_mean = [float(v) for v in t.tolist()]
+        ms_per_step, ms_ax, e2e_ms_mean, e2e_pipe_ms = [float(v) for v in t.tolist()]
 
     if rank != 0:
         if dist is not None:
@@ -280,8 +285,12 @@ def run_ours(args):
                      "cold_single_launch": {"ms_ax": ms_ax_cold, "ms_operator": ms_step_cold,
                                             "note": "one launch alone after an explicit L2 flush (write + read "
                                                     "sweep of 256 MiB), event pair around the single launch"}},
-        "e2e": {"value": dofs / (e2e_ms_mean * 1e-3) / 1e9, "unit": "GDOF/s",
-                "h2d_bytes_per_step": E * Np * 8, "d2h_bytes_per_step": E * Np * 8, "ms_per_step": e2e_ms_mean},
+        "e2e": {"value": dofs / (e2e_pipe_ms * 1e-3) / 1e9, "unit": "GDOF/s",
+                "h2d_bytes_per_step": E * Np * 8, "d2h_bytes_per_step": E * Np * 8, "ms_per_step": e2e_pipe_ms,
+                "api": "nrsb_elliptic_operator_host_async x K + nrsb_elliptic_host_wait (pinned host q in, pinned "
+                       "host Aq out every step; upload of step k+1 overlaps download of step k-1)",
+                "blocking_call": {"value": dofs / (e2e_ms_mean * 1e-3) / 1e9, "ms_per_step": e2e_ms_mean,
+                                  "api": "nrsb_elliptic_operator_host (one blocking call per step)"}},
         "gpu_launches": args.steps * bench.launches_per_step,
         "clocks": clocks, "wall_s": wall,
     }

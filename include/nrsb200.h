@@ -238,6 +238,10 @@ int nrsb_elliptic_solve_host(nrsb_elliptic_t h, const double* rhs_host, double* 
  * (0 = the fp64 solver itself when precision = 8; fp32 instances live on the MG levels) */
 int nrsb_elliptic_operator(nrsb_elliptic_t h, int level, int precision, const void* d_q, void* d_Aq, int masked);
 int nrsb_elliptic_operator_host(nrsb_elliptic_t h, const double* q_host, double* Aq_host);
+/* the same, queued: upload, operator and download of consecutive calls overlap (two staging slots, both copy
+ * engines); q_host / Aq_host should be pinned and must stay valid until nrsb_elliptic_host_wait returns */
+int nrsb_elliptic_operator_host_async(nrsb_elliptic_t h, const double* q_host, double* Aq_host);
+int nrsb_elliptic_host_wait(nrsb_elliptic_t h);
 /* ellipticAx on the full element list */
 int nrsb_elliptic_ax(nrsb_elliptic_t h, int level, int precision, const void* d_q, void* d_Aq);
 /* ellipticPreconditioner (ellipticPreconditioner.cpp:33-84) */

@@ -21,10 +21,24 @@ struct nrsb_elliptic {
   elliptic_t impl;
   dbuf<double> h2d_r, h2d_x;  // staging for the *_host entry points
   double *pin_r = nullptr, *pin_x = nullptr;
+  // pipelined host entry (operator_host_async): two staging slots, copy engines on their own streams
+  struct HostPipe {
+    dbuf<double> x[2], r[2];
+    cudaStream_t in = nullptr, out = nullptr;
+    cudaEvent_t evIn[2] = {nullptr, nullptr}, evOp[2] = {nullptr, nullptr}, evOut[2] = {nullptr, nullptr};
+    unsigned long calls = 0;
+  } pipe;
   ~nrsb_elliptic()
   {
     if (pin_r) cudaFreeHost(pin_r);
     if (pin_x) cudaFreeHost(pin_x);
+    if (pipe.in) cudaStreamDestroy(pipe.in);
+    if (pipe.out) cudaStreamDestroy(pipe.out);
+    for (int i = 0; i < 2; ++i) {
+      if (pipe.evIn[i]) cudaEventDestroy(pipe.evIn[i]);
+      if (pipe.evOp[i]) cudaEventDestroy(pipe.evOp[i]);
+      if (pipe.evOut[i]) cudaEventDestroy(pipe.evOut[i]);
+    }
   }
 };
 
@@ -277,6 +291,59 @@ int nrsb_elliptic_operator_host(nrsb_elliptic_t h, const double* q_host, double*
   if ((rc = ellipticOperator<double>(&h->impl, h->h2d_x.p, h->h2d_r.p, true))) return rc;
   NRSB_CUDA(cudaMemcpyAsync(Aq_host, h->h2d_r.p, bytes, cudaMemcpyDeviceToHost, st));
   NRSB_CUDA(cudaStreamSynchronize(st));
+  return NRSB_OK;
+}
+
+// Pipelined form of the host entry: returns as soon as the work is queued.  The upload of call k+1 runs on
+// the H2D copy engine while call k computes and call k-1 downloads on the D2H engine (PCIe is full duplex),
+// so a stream of host-resident operator applications runs at one-direction PCIe speed instead of two.
+int nrsb_elliptic_operator_host_async(nrsb_elliptic_t h, const double* q_host, double* Aq_host)
+{
+  NRSB_REQUIRE(h && q_host && Aq_host, "NULL argument");
+  auto& P = h->pipe;
+  const size_t fo = (size_t)h->impl.fieldOffset;
+  int rc;
+  if (!P.in) {
+    for (int i = 0; i < 2; ++i) {
+      if ((rc = P.x[i].alloc(fo))) return rc;
+      if ((rc = P.r[i].alloc(fo))) return rc;
+      NRSB_CUDA(cudaEventCreateWithFlags(&P.evIn[i], cudaEventDisableTiming));
+      NRSB_CUDA(cudaEventCreateWithFlags(&P.evOp[i], cudaEventDisableTiming));
+      NRSB_CUDA(cudaEventCreateWithFlags(&P.evOut[i], cudaEventDisableTiming));
+    }
+    NRSB_CUDA(cudaStreamCreateWithFlags(&P.in, cudaStreamNonBlocking));
+    NRSB_CUDA(cudaStreamCreateWithFlags(&P.out, cudaStreamNonBlocking));
+  }
+  cudaStream_t st = h->impl.stream;
+  const size_t bytes = sizeof(double) * h->impl.mesh->Nlocal;
+  const int s = (int)(P.calls & 1ul);
+  const bool reuse = P.calls >= 2;
+  if (reuse) NRSB_CUDA(cudaStreamWaitEvent(P.in, P.evOp[s], 0));  // the operator that read x[s] is done
+  NRSB_CUDA(cudaMemcpyAsync(P.x[s].p, q_host, bytes, cudaMemcpyHostToDevice, P.in));
+  NRSB_CUDA(cudaEventRecord(P.evIn[s], P.in));
+  NRSB_CUDA(cudaStreamWaitEvent(st, P.evIn[s], 0));
+  if (reuse) NRSB_CUDA(cudaStreamWaitEvent(st, P.evOut[s], 0));  // r[s] has been downloaded
+  if ((rc = ellipticOperator<double>(&h->impl, P.x[s].p, P.r[s].p, true))) return rc;
+  NRSB_CUDA(cudaEventRecord(P.evOp[s], st));
+  NRSB_CUDA(cudaStreamWaitEvent(P.out, P.evOp[s], 0));
+  NRSB_CUDA(cudaMemcpyAsync(Aq_host, P.r[s].p, bytes, cudaMemcpyDeviceToHost, P.out));
+  NRSB_CUDA(cudaEventRecord(P.evOut[s], P.out));
+  ++P.calls;
+  return NRSB_OK;
+}
+
+// Waits for every queued operator_host_async call (results are in the callers' host buffers afterwards);
+// the handle's stream is ordered after the downloads, so an event recorded on it next closes the timing.
+int nrsb_elliptic_host_wait(nrsb_elliptic_t h)
+{
+  NRSB_REQUIRE(h, "handle is NULL");
+  auto& P = h->pipe;
+  if (P.out) {
+    const unsigned long n = P.calls < 2 ? P.calls : 2;
+    for (unsigned long i = 0; i < n; ++i) NRSB_CUDA(cudaStreamWaitEvent(h->impl.stream, P.evOut[i], 0));
+    NRSB_CUDA(cudaStreamSynchronize(P.out));
+  }
+  NRSB_CUDA(cudaStreamSynchronize(h->impl.stream));
   return NRSB_OK;
 }
 

@@ -169,6 +169,13 @@ class Elliptic:
     def operator_host(self, q: np.ndarray, Aq: np.ndarray):
         call("nrsb_elliptic_operator_host", self._h, vp(q), vp(Aq))
 
+    def operator_host_async(self, q: np.ndarray, Aq: np.ndarray):
+        """Queued form: consecutive calls overlap upload / operator / download; finish with host_wait()."""
+        call("nrsb_elliptic_operator_host_async", self._h, vp(q), vp(Aq))
+
+    def host_wait(self):
+        call("nrsb_elliptic_host_wait", self._h)
+
     def ax(self, o_q, o_Aq, *, level=0, precision=8):
         call("nrsb_elliptic_ax", self._h, C.c_int(level), C.c_int(precision), vp(o_q), vp(o_Aq))
 
@@ -274,6 +281,24 @@ class OperatorBench:
         e1.record()
         e1.synchronize()
         return e0.elapsed_ms(e1)
+
+    def e2e_pipelined(self, steps):
+        """ms per step of `steps` host-to-host operator applications through the queued entry point: every
+        step uploads its own q from pinned memory and downloads its own Aq; uploads of step k+1 overlap the
+        download of step k-1 (two pinned buffer pairs alternate)."""
+        if not hasattr(self, "_hq2"):
+            fo = self.elliptic.fieldOffset
+            self._hq2 = [self.h_q, lib.PinnedBuffer(fo, np.float64)]
+            self._hA2 = [self.h_Aq, lib.PinnedBuffer(fo, np.float64)]
+            self._hq2[1].array[:] = self.h_q.array
+        e0, e1, _ = self._ev
+        e0.record()
+        for k in range(steps):
+            self.elliptic.operator_host_async(self._hq2[k & 1].array, self._hA2[k & 1].array)
+        self.elliptic.host_wait()
+        e1.record()
+        e1.synchronize()
+        return e0.elapsed_ms(e1) / steps
 
     def ncu_traffic_bytes(self):
         """dram bytes per axhelm launch from the committed ncu capture (profiles/), or None."""

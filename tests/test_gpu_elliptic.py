@@ -61,6 +61,14 @@ def test_operator_fp64(case_bp5):
     Aq = np.zeros(n)
     ell.operator_host(q, Aq)
     assert relerr(Aq, out_ref) < 1e-12
+    # queued host entry point: five different inputs in flight over two staging slots
+    qs = [q * (1.0 + k) for k in range(5)]
+    outs = [np.zeros(n) for _ in range(5)]
+    for k in range(5):
+        ell.operator_host_async(qs[k], outs[k])
+    ell.host_wait()
+    for k in range(5):
+        assert relerr(outs[k], out_ref * (1.0 + k)) < 1e-12
     # every autotuned variant gives the same answer (benchmarkAx.cpp:289-305: 400 eps)
     for v in (0, 1, 2, 3, 4, 5, 6):
         ell.set_ax_variant(8, v)
