@@ -245,6 +245,9 @@ int nrsb_elliptic_host_wait(nrsb_elliptic_t h);
 /* ellipticAx on the full element list */
 int nrsb_elliptic_ax(nrsb_elliptic_t h, int level, int precision, const void* d_q, void* d_Aq);
 /* ellipticPreconditioner (ellipticPreconditioner.cpp:33-84) */
+/* gather-scatter (+ Dirichlet mask) half of ellipticOperator alone: oogs::startFinish(o_Aq, Nfields, fieldOffset,
+ * ogsDfloat, ogsAdd, oogs) as called at ellipticOperator.cpp:164-168, preceded by ellipticApplyMask (:158) */
+int nrsb_elliptic_gather_scatter(nrsb_elliptic_t h, int level, int precision, void* d_v, int masked);
 int nrsb_elliptic_preconditioner(nrsb_elliptic_t h, double* d_r, double* d_z);
 /* pMGLevel::smoothSchwarz / smooth / coarsen / prolongate on level `level` (pfloat vectors) */
 int nrsb_elliptic_level_op(nrsb_elliptic_t h, int level, const char* op, float* d_in, float* d_out);

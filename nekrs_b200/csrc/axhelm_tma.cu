@@ -131,6 +131,9 @@ __global__ void __launch_bounds__(NGROUPS* Nq* Nq + 32, 1)
 
   const int tid = threadIdx.x;
   constexpr int nConsumers = NGROUPS * Nq2;
+  // the gather-scatter launch that follows on the stream (gs.cu / oogs.cu) may become resident next to this
+  // CTA right away: it fetches its index tables and then sleeps in griddepcontrol.wait until this grid is done
+  pdl_trigger();
   // kFused: the last F.nPush CTAs do no element work at all, they are the halo pushers (a CTA whose SM is
   // saturated by the TMA ring pays microseconds per dependent load; an otherwise idle SM does not)
   const int nAx = kFused ? (int)gridDim.x - F.nPush : (int)gridDim.x;

@@ -1,6 +1,7 @@
 // capi.cu -- extern "C" surface declared in include/nrsb200.h (kernel-level + plumbing + ogs).
 #include <cuda_profiler_api.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -20,6 +21,15 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line)
   snprintf(buf, sizeof(buf), "CUDA error %d (%s) in %s at %s:%d", (int)e, cudaGetErrorString(e), what, file, line);
   g_last_error = buf;
   return NRSB_ERR_CUDA;
+}
+
+bool pdl_enabled()
+{
+  // measured (tools/gs_timing.py, E=4096): the 255-register axhelm CTAs leave no room for co-resident
+  // gather-scatter blocks, so the early launch only perturbs block placement: operator 43.5 us with the
+  // attribute, 40.3 us without.  Off unless NRSB_PDL=1.
+  static const bool on = getenv("NRSB_PDL") != nullptr;
+  return on;
 }
 
 int ax_default_variant(int Nq, int precision)

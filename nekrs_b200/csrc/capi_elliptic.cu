@@ -358,6 +358,28 @@ int nrsb_elliptic_ax(nrsb_elliptic_t h, int level, int precision, const void* d_
              : ellipticAx<float>(e, m->Nelements, m->o_elementList.p, (const float*)d_q, (float*)d_Aq);
 }
 
+/* the gather-scatter (+ mask) half of ellipticOperator alone: oogs::startFinish(o_Aq, ..., ogsAdd) */
+int nrsb_elliptic_gather_scatter(nrsb_elliptic_t h, int level, int precision, void* d_v, int masked)
+{
+  NRSB_REQUIRE(h && d_v, "NULL argument");
+  NRSB_REQUIRE(precision == 8 || precision == 4, "precision must be 8 or 4");
+  elliptic_t* e = level_elliptic(h, level, precision);
+  NRSB_REQUIRE(e, "no such level");
+  const dlong nm = masked ? e->Nmasked : 0;
+  if (e->oogs->ogs->NhaloGather && nm) {
+    int rc = precision == 8 ? mask_launch<double>(nm, e->o_maskIds.p, (double*)d_v, e->stream)
+                            : mask_launch<float>(nm, e->o_maskIds.p, (float*)d_v, e->stream);
+    if (rc) return rc;
+    return precision == 8
+               ? e->oogs->startFinish<double>((double*)d_v, e->Nfields, e->fieldOffset, gs_op::add, 0, nullptr, e->stream)
+               : e->oogs->startFinish<float>((float*)d_v, e->Nfields, e->fieldOffset, gs_op::add, 0, nullptr, e->stream);
+  }
+  return precision == 8 ? e->oogs->startFinish<double>((double*)d_v, e->Nfields, e->fieldOffset, gs_op::add, nm,
+                                                       e->o_maskIds.p, e->stream)
+                        : e->oogs->startFinish<float>((float*)d_v, e->Nfields, e->fieldOffset, gs_op::add, nm,
+                                                      e->o_maskIds.p, e->stream);
+}
+
 int nrsb_elliptic_preconditioner(nrsb_elliptic_t h, double* d_r, double* d_z)
 {
   NRSB_REQUIRE(h && d_r && d_z, "NULL argument");

@@ -46,6 +46,32 @@ struct DMat {
   T v[Nq * Nq];  // row-major D[i][m] = l_m'(r_i)
 };
 
+// Programmatic dependent launch (sm_90+): a kernel launched with launch_pdl() may become resident while the
+// previous kernel of the stream is still running (once every CTA of that kernel has executed pdl_trigger(),
+// or exited).  Everything before pdl_wait() must not touch data the previous kernel writes; pdl_wait()
+// returns when the previous kernel has completed and its stores are visible.  Launch latency, block
+// scheduling and the index-table loads of the dependent kernel are thereby hidden behind the producer.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();  // NRSB_PDL=1 turns the attribute on (A/B timing; see capi.cu)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args)
+{
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 template <typename T>
 __device__ __forceinline__ T ldg_stream(const T* p)
 {

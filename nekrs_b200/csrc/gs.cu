@@ -16,73 +16,118 @@
 // The mask (q[maskIds[n]] = 0) is folded into the same launch: masked nodes carry global id 0 in
 // the masked ogs handle (ellipticOgs.cpp:126-131) and therefore belong to no row, so zeroing them
 // commutes with the sums.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "gs.hpp"
 
 namespace nrsb {
 
-template <typename T>
-__global__ void __launch_bounds__(kBlockSize)
-    gs_rows_kernel(const GsRowsDev R, const int Nfields, const dlong stride, T* __restrict__ q)
+// One row of the bucketed table, fetched BEFORE the data is ready (the table does not depend on it).
+// n = number of copies (ids in id[0..n)), n = 1: a masked node (store zero), n = -1: general CSR row
+// [id[0], id[1]) of genIds (more than 8 copies: not on a conforming hex mesh interior, kept for generality).
+struct GsRowRef {
+  int n;
+  int id[8];
+};
+
+__device__ __forceinline__ GsRowRef gs_row_fetch(const GsRowsDev& R, long m)
 {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  T* __restrict__ qf = q + (size_t)blockIdx.y * stride;
-  (void)Nfields;
-  if (n < R.nPairs) {
-    const int2 id = R.pairs[n];
-    T s = T(0);
-    s += qf[id.x];
-    s += qf[id.y];
-    qf[id.x] = s;
-    qf[id.y] = s;
-    return;
+  GsRowRef r;
+  r.n = 0;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) r.id[c] = 0;
+  if (m < R.nPairs) {
+    const int2 id = R.pairs[m];
+    r.n = 2;
+    r.id[0] = id.x;
+    r.id[1] = id.y;
+    return r;
   }
-  int m = n - R.nPairs;
+  m -= R.nPairs;
   if (m < R.nQuads) {
     const int4 id = R.quads[m];
-    T s = T(0);
-    s += qf[id.x];
-    s += qf[id.y];
-    s += qf[id.z];
-    s += qf[id.w];
-    qf[id.x] = s;
-    qf[id.y] = s;
-    qf[id.z] = s;
-    qf[id.w] = s;
-    return;
+    r.n = 4;
+    r.id[0] = id.x;
+    r.id[1] = id.y;
+    r.id[2] = id.z;
+    r.id[3] = id.w;
+    return r;
   }
   m -= R.nQuads;
   if (m < R.nOcts) {
     const int4 ia = R.octs[2 * m], ib = R.octs[2 * m + 1];
-    T s = T(0);
-    s += qf[ia.x];
-    s += qf[ia.y];
-    s += qf[ia.z];
-    s += qf[ia.w];
-    s += qf[ib.x];
-    s += qf[ib.y];
-    s += qf[ib.z];
-    s += qf[ib.w];
-    qf[ia.x] = s;
-    qf[ia.y] = s;
-    qf[ia.z] = s;
-    qf[ia.w] = s;
-    qf[ib.x] = s;
-    qf[ib.y] = s;
-    qf[ib.z] = s;
-    qf[ib.w] = s;
-    return;
+    r.n = 8;
+    r.id[0] = ia.x;
+    r.id[1] = ia.y;
+    r.id[2] = ia.z;
+    r.id[3] = ia.w;
+    r.id[4] = ib.x;
+    r.id[5] = ib.y;
+    r.id[6] = ib.z;
+    r.id[7] = ib.w;
+    return r;
   }
   m -= R.nOcts;
   if (m < R.nGen) {
-    const int start = R.genStarts[m], end = R.genStarts[m + 1];
-    T s = T(0);
-    for (int c = start; c < end; ++c) s += qf[R.genIds[c]];
-    for (int c = start; c < end; ++c) qf[R.genIds[c]] = s;
-    return;
+    r.n = -1;
+    r.id[0] = R.genStarts[m];
+    r.id[1] = R.genStarts[m + 1];
+    return r;
   }
   m -= R.nGen;
-  if (m < R.nMasked) qf[R.maskIds[m]] = T(0);
+  if (m < R.nMasked) {
+    r.n = 1;
+    r.id[0] = R.maskIds[m];
+  }
+  return r;
+}
+
+// kRPT rows per thread.  All value loads of all rows of a thread are issued (predicated, no branches) before
+// the first add, so a thread has up to 8 kRPT independent loads in flight.  Copies are summed in ascending
+// local index, as the reference's CSR loop does (bit-identical sums).
+// The kernel is launched as a programmatic dependent launch: blocks may become resident while the producer
+// (axhelm) is still running, fetch their index entries, and sleep in pdl_wait() until its stores are visible.
+template <typename T, int kRPT>
+__global__ void __launch_bounds__(kBlockSize)
+    gs_rows_kernel(const GsRowsDev R, const int Nfields, const dlong stride, T* __restrict__ q)
+{
+  (void)Nfields;
+  T* __restrict__ qf = q + (size_t)blockIdx.y * stride;
+  GsRowRef r[kRPT];
+#pragma unroll
+  for (int j = 0; j < kRPT; ++j) r[j] = gs_row_fetch(R, ((long)blockIdx.x * kRPT + j) * blockDim.x + threadIdx.x);
+  pdl_wait();
+  T v[kRPT][8];
+#pragma unroll
+  for (int j = 0; j < kRPT; ++j)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) v[j][c] = (c < r[j].n && r[j].n > 1) ? qf[r[j].id[c]] : T(0);
+#pragma unroll
+  for (int j = 0; j < kRPT; ++j) {
+    T s = T(0);
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      if (c < r[j].n) s += v[j][c];
+    if (r[j].n == 1) s = T(0);  // masked node
+    if (r[j].n == -1) {
+      for (int c = r[j].id[0]; c < r[j].id[1]; ++c) s += qf[R.genIds[c]];
+      for (int c = r[j].id[0]; c < r[j].id[1]; ++c) qf[R.genIds[c]] = s;
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      if (c < r[j].n) qf[r[j].id[c]] = s;
+  }
+}
+
+int gs_rows_per_thread()
+{
+  static const int rpt = [] {
+    const char* e = getenv("NRSB_GS_RPT");
+    const int v = e ? atoi(e) : 1;
+    return (v == 2 || v == 4) ? v : 1;
+  }();
+  return rpt;
 }
 
 template <typename T>
@@ -90,9 +135,11 @@ int gs_rows_launch(const GsRowsDev& R, int Nfields, dlong stride, T* q, cudaStre
 {
   const long total = (long)R.nPairs + R.nQuads + R.nOcts + R.nGen + R.nMasked;
   if (total == 0 || Nfields == 0) return NRSB_OK;
-  dim3 grid((unsigned)((total + kBlockSize - 1) / kBlockSize), Nfields);
-  gs_rows_kernel<T><<<grid, kBlockSize, 0, stream>>>(R, Nfields, stride, q);
-  NRSB_CHECK_LAUNCH();
+  const int rpt = gs_rows_per_thread();
+  const long perBlock = (long)kBlockSize * rpt;
+  dim3 grid((unsigned)((total + perBlock - 1) / perBlock), Nfields);
+  auto kern = rpt == 1 ? gs_rows_kernel<T, 1> : (rpt == 2 ? gs_rows_kernel<T, 2> : gs_rows_kernel<T, 4>);
+  NRSB_CUDA(launch_pdl(kern, grid, dim3(kBlockSize), 0, stream, R, Nfields, stride, q));
   return NRSB_OK;
 }
 template int gs_rows_launch<double>(const GsRowsDev&, int, dlong, double*, cudaStream_t);

@@ -179,6 +179,11 @@ class Elliptic:
     def ax(self, o_q, o_Aq, *, level=0, precision=8):
         call("nrsb_elliptic_ax", self._h, C.c_int(level), C.c_int(precision), vp(o_q), vp(o_Aq))
 
+    def gather_scatter(self, o_v, *, level=0, precision=8, masked=True):
+        """mask + oogs::startFinish(o_v, ogsAdd): the second half of ellipticOperator alone."""
+        call("nrsb_elliptic_gather_scatter", self._h, C.c_int(level), C.c_int(precision), vp(o_v),
+             C.c_int(1 if masked else 0))
+
     def preconditioner(self, o_r, o_z):
         call("nrsb_elliptic_preconditioner", self._h, vp(o_r), vp(o_z))
 
@@ -245,6 +250,11 @@ class OperatorBench:
         ell, q, Aq = self.sets[self._k % len(self.sets)]
         self._k += 1
         ell.ax(q, Aq)
+
+    def gs_only(self):
+        ell, q, Aq = self.sets[self._k % len(self.sets)]
+        self._k += 1
+        ell.gather_scatter(Aq)
 
     def timed_loop(self, fn, steps):
         """ms per call of `fn` over `steps` back-to-back calls (one event pair, launching stream)."""
