@@ -10,7 +10,10 @@
 // keeps HBM busy through all phases (ncu of variant 1: DRAM 43 %, occupancy-limited).
 //
 // Same arithmetic order as variant 1 => identical results.
+#include <cstdlib>
+
 #include "common.cuh"
+#include "gs.hpp"
 #include "halo.cuh"
 
 namespace nrsb {
@@ -79,6 +82,119 @@ __device__ __forceinline__ void group_sync(int id, int nthreads)
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// ---- phase 2 of the kGs launch: this thread's share of the on-rank gather rows and masked nodes.
+// Thread `gt` of `nT`; rows are dealt round-robin so that neighbouring lanes read neighbouring table entries.
+// The table entries of the first batch (kGsP pair rows + kGsQ quad rows per thread: everything a 4096-element
+// box needs) are fetched BEFORE the device-wide barrier, so that after it one round of value loads (L2, __ldcg:
+// other SMs stored them) and the stores remain.  Copies are summed in ascending local index, the reference's
+// order (gatherScatterMany.okl), so the result is bit-identical to the separate kernel's.
+constexpr int kGsP = 20;
+constexpr int kGsQ = 4;
+struct GsPrefetch {
+  int2 p[kGsP];
+  int4 q[kGsQ];
+};
+
+__device__ __forceinline__ void gs_phase_prefetch(const GsRowsDev& R, const int gt, const int nT, GsPrefetch& F)
+{
+#pragma unroll
+  for (int j = 0; j < kGsP; ++j) {
+    const int i = gt + j * nT;
+    F.p[j] = i < R.nPairs ? __ldg(R.pairs + i) : make_int2(-1, -1);
+  }
+#pragma unroll
+  for (int j = 0; j < kGsQ; ++j) {
+    const int i = gt + j * nT;
+    F.q[j] = i < R.nQuads ? __ldg(R.quads + i) : make_int4(-1, -1, -1, -1);
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ void gs_phase_rows(const GsRowsDev& R, const int gt, const int nT, T* __restrict__ q,
+                                              GsPrefetch& F)
+{
+  for (int it = 0; (long)it * kGsP * nT < R.nPairs || (long)it * kGsQ * nT < R.nQuads; ++it) {
+    if (it > 0) {  // later batches (larger meshes): same code, entries fetched here
+#pragma unroll
+      for (int j = 0; j < kGsP; ++j) {
+        const long i = gt + ((long)it * kGsP + j) * nT;
+        F.p[j] = i < R.nPairs ? __ldg(R.pairs + i) : make_int2(-1, -1);
+      }
+#pragma unroll
+      for (int j = 0; j < kGsQ; ++j) {
+        const long i = gt + ((long)it * kGsQ + j) * nT;
+        F.q[j] = i < R.nQuads ? __ldg(R.quads + i) : make_int4(-1, -1, -1, -1);
+      }
+    }
+    T a[kGsP], b[kGsP], v[kGsQ][4];
+#pragma unroll
+    for (int j = 0; j < kGsP; ++j)
+      if (F.p[j].x >= 0) {
+        a[j] = __ldcg(q + F.p[j].x);
+        b[j] = __ldcg(q + F.p[j].y);
+      }
+#pragma unroll
+    for (int j = 0; j < kGsQ; ++j)
+      if (F.q[j].x >= 0) {
+        v[j][0] = __ldcg(q + F.q[j].x);
+        v[j][1] = __ldcg(q + F.q[j].y);
+        v[j][2] = __ldcg(q + F.q[j].z);
+        v[j][3] = __ldcg(q + F.q[j].w);
+      }
+#pragma unroll
+    for (int j = 0; j < kGsP; ++j)
+      if (F.p[j].x >= 0) {
+        T sum = T(0);
+        sum += a[j];
+        sum += b[j];
+        q[F.p[j].x] = sum;
+        q[F.p[j].y] = sum;
+      }
+#pragma unroll
+    for (int j = 0; j < kGsQ; ++j)
+      if (F.q[j].x >= 0) {
+        T sum = T(0);
+        sum += v[j][0];
+        sum += v[j][1];
+        sum += v[j][2];
+        sum += v[j][3];
+        q[F.q[j].x] = sum;
+        q[F.q[j].y] = sum;
+        q[F.q[j].z] = sum;
+        q[F.q[j].w] = sum;
+      }
+  }
+  for (int i = gt; i < R.nOcts; i += nT) {
+    const int4 ia = __ldg(R.octs + 2 * i), ib = __ldg(R.octs + 2 * i + 1);
+    const T v0 = __ldcg(q + ia.x), v1 = __ldcg(q + ia.y), v2 = __ldcg(q + ia.z), v3 = __ldcg(q + ia.w);
+    const T v4 = __ldcg(q + ib.x), v5 = __ldcg(q + ib.y), v6 = __ldcg(q + ib.z), v7 = __ldcg(q + ib.w);
+    T sum = T(0);
+    sum += v0;
+    sum += v1;
+    sum += v2;
+    sum += v3;
+    sum += v4;
+    sum += v5;
+    sum += v6;
+    sum += v7;
+    q[ia.x] = sum;
+    q[ia.y] = sum;
+    q[ia.z] = sum;
+    q[ia.w] = sum;
+    q[ib.x] = sum;
+    q[ib.y] = sum;
+    q[ib.z] = sum;
+    q[ib.w] = sum;
+  }
+  for (int i = gt; i < R.nGen; i += nT) {
+    const int s0 = __ldg(R.genStarts + i), s1 = __ldg(R.genStarts + i + 1);
+    T sum = T(0);
+    for (int c = s0; c < s1; ++c) sum += __ldcg(q + __ldg(R.genIds + c));
+    for (int c = s0; c < s1; ++c) q[__ldg(R.genIds + c)] = sum;
+  }
+  for (int i = gt; i < R.nMasked; i += nT) q[__ldg(R.maskIds + i)] = T(0);
+}
+
 template <typename T, int Nq>
 struct SlabT {
   static constexpr int bankMod = 32 / (sizeof(T) / 4);
@@ -108,11 +224,14 @@ struct SlabT {
 // co-resident (grid = #SMs, one CTA per SM), so the wait cannot deadlock; it is bounded anyway.
 // (Measured: a service warp inside a working CTA needs ~20 us for the push, each dependent access queues
 // behind that SM's 200 KB of in-flight bulk copies; dedicated CTAs need ~5 us.)
-template <typename T, int Nq, int NGROUPS, int NSTAGES, bool kPoisson, bool kFused>
+//
+// kGs: ellipticOperator's mask + on-rank gather-scatter (ellipticOperator.cpp:158-168) become phase 2 of the same
+// launch (struct FusedRows, gs.hpp): no kernel boundary, no second launch, row tables fetched while waiting.
+template <typename T, int Nq, int NGROUPS, int NSTAGES, bool kPoisson, bool kFused, bool kGs>
 __global__ void __launch_bounds__(NGROUPS* Nq* Nq + 32, 1)
     ax_tma_kernel(const dlong Nelements, const dlong* __restrict__ elementList, const T* __restrict__ ggeo,
                   const DMat<T, Nq> Dm, const T* __restrict__ lambda0, const T* __restrict__ lambda1,
-                  const T* __restrict__ q, T* __restrict__ Aq, const FusedHalo F)
+                  const T* __restrict__ q, T* __restrict__ Aq, const FusedHalo F, const FusedRows R2)
 {
   constexpr int Np = Nq * Nq * Nq;
   constexpr int Nq2 = Nq * Nq;
@@ -332,18 +451,39 @@ __global__ void __launch_bounds__(NGROUPS* Nq* Nq + 32, 1)
     group_sync(1 + g, Nq2);  // su/ss are rewritten by the next element of this group
     if (haloElem && t == 0) atomicAdd(F.counter, 1ull);
   }
+
+  if constexpr (kGs) {
+    // ===== phase 2: mask + on-rank gather-scatter by the consumer threads of all axhelm CTAs =====
+    const int nT = nAx * nConsumers;
+    const int gt = blockIdx.x * nConsumers + tid;  // a warp reads 32 consecutive table entries
+    GsPrefetch pre;
+    gs_phase_prefetch(R2.R, gt, nT, pre);
+    group_sync(15, nConsumers);
+    if (tid == 0) {
+      __threadfence();  // the CTA's stores (ordered before the barrier above) become visible device-wide
+      atomicAdd(R2.arrive, 1ull);
+      const long long t0 = clock64();
+      while (ld_acquire_u64(R2.arrive) < R2.target) {
+        __nanosleep(32);
+        if (clock64() - t0 > (1ll << 33)) break;  // ~4 s: never reached unless co-residency was violated
+      }
+    }
+    group_sync(15, nConsumers);
+    gs_phase_rows<T>(R2.R, gt, nT, Aq, pre);
+  }
 }
 
-template <typename T, int Nq, int NGROUPS, int NSTAGES, bool kPoisson, bool kFused = false>
+template <typename T, int Nq, int NGROUPS, int NSTAGES, bool kPoisson, bool kFused = false, bool kGs = false>
 static int launch_tma(dlong Nelements, const dlong* elementList, const T* ggeo, const T* D_host, const T* lambda0,
-                      const T* lambda1, const T* q, T* Aq, cudaStream_t stream, const FusedHalo* fused = nullptr)
+                      const T* lambda1, const T* q, T* Aq, cudaStream_t stream, const FusedHalo* fused = nullptr,
+                      FusedRows* rows = nullptr)
 {
   constexpr int Np = Nq * Nq * Nq;
   constexpr int NG = kPoisson ? 6 : 7;
   using S = SlabT<T, Nq>;
   const size_t smem = ((size_t)NSTAGES * (NG + 1) * Np + (size_t)NGROUPS * 3 * S::size) * sizeof(T) +
                       2 * NSTAGES * sizeof(uint64_t) + 128;
-  auto kern = ax_tma_kernel<T, Nq, NGROUPS, NSTAGES, kPoisson, kFused>;
+  auto kern = ax_tma_kernel<T, Nq, NGROUPS, NSTAGES, kPoisson, kFused, kGs>;
   static bool configured = false;
   if (!configured) {
     NRSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -355,8 +495,17 @@ static int launch_tma(dlong Nelements, const dlong* elementList, const T* ggeo, 
   if (grid > Nelements) grid = Nelements;
   const FusedHalo F = fused ? *fused : FusedHalo();
   if (kFused) grid = kNumSMs;  // pushers + workers, all co-resident
-  kern<<<grid, NGROUPS * Nq * Nq + 32, smem, stream>>>(Nelements, elementList, ggeo, Dm, lambda0,
-                                                                        lambda1, q, Aq, F);
+  FusedRows R2;
+  if (kGs) {
+    R2 = *rows;
+    R2.target += (unsigned long long)(kFused ? grid - F.nPush : grid);  // every axhelm CTA arrives once
+    rows->target = R2.target;
+  }
+  // (Launching this kernel as a programmatic dependent launch, with the first geometric-factor slabs requested
+  // before griddepcontrol.wait, was measured slower: 28-29 us per launch with the attribute, 31-33 us without it,
+  // against 26.7 us for the plain launch -- the wait itself resolves late.)
+  kern<<<grid, NGROUPS * Nq * Nq + 32, smem, stream>>>(Nelements, elementList, ggeo, Dm, lambda0, lambda1, q, Aq, F,
+                                                       R2);
   NRSB_CHECK_LAUNCH();
   return NRSB_OK;
 }
@@ -409,6 +558,37 @@ int ax_tma_fused_launch(int Nq, int variant, dlong Nelements, const dlong* eleme
   NRSB_TMAF(6, 12)
 #undef NRSB_TMAF
 }
+// Ax + mask + on-rank gather-scatter in ONE launch (single rank: the whole ellipticOperator; several ranks:
+// halo rows are pushed by the pusher CTAs and folded by oogs::finish).  rows->target is advanced.
+template <typename T>
+int ax_tma_gs_launch(int Nq, dlong Nelements, const dlong* elementList, const T* ggeo, const T* D_host,
+                     const T* lambda0, const T* lambda1, int poisson, const T* q, T* Aq, const FusedHalo* F,
+                     FusedRows* rows, cudaStream_t stream)
+{
+  if (Nelements == 0) return NRSB_OK;
+  if (Nq != 8) {
+    set_last_error("fused axhelm + gather-scatter is built for Nq = 8 only");
+    return NRSB_ERR_INVALID;
+  }
+#define NRSB_TMAG(G_, S_, FUSED)                                                                                   \
+  return poisson ? launch_tma<T, 8, G_, S_, true, FUSED, true>(Nelements, elementList, ggeo, D_host, lambda0, lambda1, \
+                                                              q, Aq, stream, F, rows)                                \
+                 : launch_tma<T, 8, G_, S_, false, FUSED, true>(Nelements, elementList, ggeo, D_host, lambda0,       \
+                                                               lambda1, q, Aq, stream, F, rows);
+  if (F) {
+    if (sizeof(T) == 8) { NRSB_TMAG(3, 6, true) }
+    NRSB_TMAG(6, 12, true)
+  }
+  if (sizeof(T) == 8) { NRSB_TMAG(3, 6, false) }
+  NRSB_TMAG(6, 12, false)
+#undef NRSB_TMAG
+}
+template int ax_tma_gs_launch<double>(int, dlong, const dlong*, const double*, const double*, const double*,
+                                      const double*, int, const double*, double*, const FusedHalo*, FusedRows*,
+                                      cudaStream_t);
+template int ax_tma_gs_launch<float>(int, dlong, const dlong*, const float*, const float*, const float*, const float*,
+                                     int, const float*, float*, const FusedHalo*, FusedRows*, cudaStream_t);
+
 template int ax_tma_fused_launch<double>(int, int, dlong, const dlong*, const double*, const double*, const double*,
                                          const double*, int, const double*, double*, const FusedHalo&, cudaStream_t);
 template int ax_tma_fused_launch<float>(int, int, dlong, const dlong*, const float*, const float*, const float*,

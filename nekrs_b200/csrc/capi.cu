@@ -23,13 +23,16 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line)
   return NRSB_ERR_CUDA;
 }
 
-bool pdl_enabled()
+bool pdl_enabled(bool producer)
 {
-  // measured (tools/gs_timing.py, E=4096): the 255-register axhelm CTAs leave no room for co-resident
-  // gather-scatter blocks, so the early launch only perturbs block placement: operator 43.5 us with the
-  // attribute, 40.3 us without.  Off unless NRSB_PDL=1.
-  static const bool on = getenv("NRSB_PDL") != nullptr;
-  return on;
+  // producer = a persistent kernel launched behind any kernel (not used at present; axhelm_tma.cu documents
+  // the measurement that ruled it out for axhelm): off unless NRSB_PDL_AX=1.
+  // consumer = gather-scatter launches behind axhelm: measured (tools/gs_timing.py, E=4096) the 255-register
+  // axhelm CTAs leave no room for co-resident gather-scatter blocks, so the early launch only perturbs block
+  // placement (operator 43.5 us with the attribute, 40.3 us without): off unless NRSB_PDL_GS=1.
+  static const bool ax = getenv("NRSB_PDL_AX") != nullptr;
+  static const bool gs = getenv("NRSB_PDL_GS") != nullptr;
+  return producer ? ax : gs;
 }
 
 int ax_default_variant(int Nq, int precision)

@@ -53,11 +53,11 @@ struct DMat {
 // scheduling and the index-table loads of the dependent kernel are thereby hidden behind the producer.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-bool pdl_enabled();  // NRSB_PDL=1 turns the attribute on (A/B timing; see capi.cu)
+bool pdl_enabled(bool producer);  // see capi.cu
 
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
-                              Args&&... args)
+inline cudaError_t launch_pdl_if(bool on, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                 cudaStream_t stream, Args&&... args)
 {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
@@ -68,8 +68,22 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = on ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+// launch_pdl: the persistent axhelm kernel (its prologue and geometric-factor prefetch overlap the tail of the
+// previous kernel); launch_pdl_consumer: gather-scatter style kernels behind axhelm (off by default, see capi.cu)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args)
+{
+  return launch_pdl_if(pdl_enabled(true), kernel, grid, block, smem, stream, static_cast<Args&&>(args)...);
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl_consumer(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                       cudaStream_t stream, Args&&... args)
+{
+  return launch_pdl_if(pdl_enabled(false), kernel, grid, block, smem, stream, static_cast<Args&&>(args)...);
 }
 
 template <typename T>

@@ -178,6 +178,29 @@ int ellipticOperator(elliptic_t* elliptic, const T* o_q, T* o_Aq, bool masked)
   int rc;
   const dlong nm = masked ? elliptic->Nmasked : 0;
   using P = prec_traits<T>;
+  const int axv = elliptic->ax_variant[P::idx] < 0 ? ax_default_variant(mesh->Nq, (int)sizeof(T))
+                                                   : elliptic->ax_variant[P::idx];
+  const bool gsInLaunch = elliptic->fusedGsAx && mesh->Nq == 8 && elliptic->Nfields == 1 && axv >= 4;
+  FusedRows FR;
+  if (gsInLaunch) {
+    if (!elliptic->fusedArrive.p) {
+      if ((rc = elliptic->fusedArrive.alloc(1))) return rc;  // zero-initialised
+      NRSB_CUDA(cudaDeviceSynchronize());
+    }
+    FR.R = oogs->ogs->rows;
+    FR.R.nMasked = nm;
+    FR.R.maskIds = elliptic->o_maskIds.p;
+    FR.arrive = elliptic->fusedArrive.p;
+    FR.target = elliptic->fusedArriveTarget;
+  }
+  if (gsInLaunch && oogs->ogs->NhaloGather == 0) {
+    // single rank: the whole operator (Ax, mask, gather-scatter) is ONE launch
+    rc = ax_tma_gs_launch<T>(mesh->Nq, mesh->Nelements, mesh->o_elementList.p, P::ggeo(mesh), P::D(mesh),
+                             P::lambda0(elliptic), P::lambda1(elliptic), elliptic->poisson ? 1 : 0, o_q, o_Aq, nullptr,
+                             &FR, elliptic->stream);
+    elliptic->fusedArriveTarget = FR.target;
+    return rc;
+  }
   if (elliptic->overlap && elliptic->fusedHaloAx && mesh->Nq == 8 && elliptic->Nfields == 1 &&
       elliptic->ax_variant[P::idx] != 0 && mesh->NglobalGatherElements > 0 && oogs->peers.size() <= 32) {
     // ONE launch: Ax over [halo elements, interior elements]; a service warp per CTA pushes the halo partial
@@ -376,6 +399,10 @@ int ellipticSolveSetup(elliptic_t* elliptic)
   // ENABLE GS COMM OVERLAP: the reference times both variants and keeps the faster
   // (ellipticSetup.cpp:278-302).  Splitting only pays when there are halo rows.
   elliptic->fusedHaloAx = !options.compareArgs("FUSED HALO AX", "FALSE");
+  // measured (tools/gs_timing.py, B200): phase 2 with 192 threads per SM needs 15 us for the rows the separate
+  // 2048-threads-per-SM kernel does in 12.5 us (both bound by LSU wavefronts of the scattered 8-byte accesses),
+  // 42.0 vs 39.4 us per operator at E=4096: off unless asked for
+  elliptic->fusedGsAx = options.compareArgs("FUSED GS AX", "TRUE") || getenv("NRSB_FUSED_GS") != nullptr;
   elliptic->overlap = elliptic->ogs->NhaloGather > 0 && !options.compareArgs("ENABLE GS COMM OVERLAP", "FALSE") &&
                       mesh->NlocalGatherElements > 0;
 

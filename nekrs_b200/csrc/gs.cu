@@ -23,66 +23,6 @@
 
 namespace nrsb {
 
-// One row of the bucketed table, fetched BEFORE the data is ready (the table does not depend on it).
-// n = number of copies (ids in id[0..n)), n = 1: a masked node (store zero), n = -1: general CSR row
-// [id[0], id[1]) of genIds (more than 8 copies: not on a conforming hex mesh interior, kept for generality).
-struct GsRowRef {
-  int n;
-  int id[8];
-};
-
-__device__ __forceinline__ GsRowRef gs_row_fetch(const GsRowsDev& R, long m)
-{
-  GsRowRef r;
-  r.n = 0;
-#pragma unroll
-  for (int c = 0; c < 8; ++c) r.id[c] = 0;
-  if (m < R.nPairs) {
-    const int2 id = R.pairs[m];
-    r.n = 2;
-    r.id[0] = id.x;
-    r.id[1] = id.y;
-    return r;
-  }
-  m -= R.nPairs;
-  if (m < R.nQuads) {
-    const int4 id = R.quads[m];
-    r.n = 4;
-    r.id[0] = id.x;
-    r.id[1] = id.y;
-    r.id[2] = id.z;
-    r.id[3] = id.w;
-    return r;
-  }
-  m -= R.nQuads;
-  if (m < R.nOcts) {
-    const int4 ia = R.octs[2 * m], ib = R.octs[2 * m + 1];
-    r.n = 8;
-    r.id[0] = ia.x;
-    r.id[1] = ia.y;
-    r.id[2] = ia.z;
-    r.id[3] = ia.w;
-    r.id[4] = ib.x;
-    r.id[5] = ib.y;
-    r.id[6] = ib.z;
-    r.id[7] = ib.w;
-    return r;
-  }
-  m -= R.nOcts;
-  if (m < R.nGen) {
-    r.n = -1;
-    r.id[0] = R.genStarts[m];
-    r.id[1] = R.genStarts[m + 1];
-    return r;
-  }
-  m -= R.nGen;
-  if (m < R.nMasked) {
-    r.n = 1;
-    r.id[0] = R.maskIds[m];
-  }
-  return r;
-}
-
 // kRPT rows per thread.  All value loads of all rows of a thread are issued (predicated, no branches) before
 // the first add, so a thread has up to 8 kRPT independent loads in flight.  Copies are summed in ascending
 // local index, as the reference's CSR loop does (bit-identical sums).
@@ -93,6 +33,7 @@ __global__ void __launch_bounds__(kBlockSize)
     gs_rows_kernel(const GsRowsDev R, const int Nfields, const dlong stride, T* __restrict__ q)
 {
   (void)Nfields;
+  pdl_trigger();  // a persistent axhelm launch behind this kernel may start its prologue on drained SMs
   T* __restrict__ qf = q + (size_t)blockIdx.y * stride;
   GsRowRef r[kRPT];
 #pragma unroll
@@ -139,7 +80,7 @@ int gs_rows_launch(const GsRowsDev& R, int Nfields, dlong stride, T* q, cudaStre
   const long perBlock = (long)kBlockSize * rpt;
   dim3 grid((unsigned)((total + perBlock - 1) / perBlock), Nfields);
   auto kern = rpt == 1 ? gs_rows_kernel<T, 1> : (rpt == 2 ? gs_rows_kernel<T, 2> : gs_rows_kernel<T, 4>);
-  NRSB_CUDA(launch_pdl(kern, grid, dim3(kBlockSize), 0, stream, R, Nfields, stride, q));
+  NRSB_CUDA(launch_pdl_consumer(kern, grid, dim3(kBlockSize), 0, stream, R, Nfields, stride, q));
   return NRSB_OK;
 }
 template int gs_rows_launch<double>(const GsRowsDev&, int, dlong, double*, cudaStream_t);

@@ -21,6 +21,78 @@ struct GsRowsDev {
   const int* maskIds = nullptr;
 };
 
+#ifdef __CUDACC__
+// One row of the bucketed table, fetched BEFORE the data is ready (the table does not depend on it).
+// n = number of copies (ids in id[0..n)), n = 1: a masked node (store zero), n = -1: general CSR row
+// [id[0], id[1]) of genIds (more than 8 copies: not on a conforming hex mesh interior, kept for generality).
+struct GsRowRef {
+  int n;
+  int id[8];
+};
+
+__device__ __forceinline__ GsRowRef gs_row_fetch(const GsRowsDev& R, long m)
+{
+  GsRowRef r;
+  r.n = 0;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) r.id[c] = 0;
+  if (m < R.nPairs) {
+    const int2 id = R.pairs[m];
+    r.n = 2;
+    r.id[0] = id.x;
+    r.id[1] = id.y;
+    return r;
+  }
+  m -= R.nPairs;
+  if (m < R.nQuads) {
+    const int4 id = R.quads[m];
+    r.n = 4;
+    r.id[0] = id.x;
+    r.id[1] = id.y;
+    r.id[2] = id.z;
+    r.id[3] = id.w;
+    return r;
+  }
+  m -= R.nQuads;
+  if (m < R.nOcts) {
+    const int4 ia = R.octs[2 * m], ib = R.octs[2 * m + 1];
+    r.n = 8;
+    r.id[0] = ia.x;
+    r.id[1] = ia.y;
+    r.id[2] = ia.z;
+    r.id[3] = ia.w;
+    r.id[4] = ib.x;
+    r.id[5] = ib.y;
+    r.id[6] = ib.z;
+    r.id[7] = ib.w;
+    return r;
+  }
+  m -= R.nOcts;
+  if (m < R.nGen) {
+    r.n = -1;
+    r.id[0] = R.genStarts[m];
+    r.id[1] = R.genStarts[m + 1];
+    return r;
+  }
+  m -= R.nGen;
+  if (m < R.nMasked) {
+    r.n = 1;
+    r.id[0] = R.maskIds[m];
+  }
+  return r;
+}
+
+#endif
+
+// the on-rank gather-scatter + mask as phase 2 of the persistent axhelm launch (axhelm_tma.cu): every axhelm CTA
+// arrives at a device-wide counter once its elements are stored, waits for the others, then takes its share of
+// the bucketed rows.  Replaces the kernel boundary + second launch of ellipticOperator (ellipticOperator.cpp:158-168).
+struct FusedRows {
+  GsRowsDev R;
+  unsigned long long* arrive = nullptr;  // monotone arrival counter of the axhelm CTAs
+  unsigned long long target = 0;         // its value once every axhelm CTA of this launch has arrived
+};
+
 template <typename T>
 int gs_rows_launch(const GsRowsDev& R, int Nfields, dlong stride, T* q, cudaStream_t stream);
 template <typename T>

