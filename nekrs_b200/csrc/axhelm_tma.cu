@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "gs.hpp"
 #include "halo.cuh"
+#include "kernels.hpp"
 
 namespace nrsb {
 
@@ -227,7 +228,7 @@ struct SlabT {
 //
 // kGs: ellipticOperator's mask + on-rank gather-scatter (ellipticOperator.cpp:158-168) become phase 2 of the same
 // launch (struct FusedRows, gs.hpp): no kernel boundary, no second launch, row tables fetched while waiting.
-template <typename T, int Nq, int NGROUPS, int NSTAGES, bool kPoisson, bool kFused, bool kGs>
+template <typename T, int Nq, int NGROUPS, int NSTAGES, bool kPoisson, bool kFused, bool kGs, bool kDot>
 __global__ void __launch_bounds__(NGROUPS* Nq* Nq + 32, 1)
     ax_tma_kernel(const dlong Nelements, const dlong* __restrict__ elementList, const T* __restrict__ ggeo,
                   const DMat<T, Nq> Dm, const T* __restrict__ lambda0, const T* __restrict__ lambda1,
@@ -270,6 +271,7 @@ __global__ void __launch_bounds__(NGROUPS* Nq* Nq + 32, 1)
   __syncthreads();
 
   if (pusher) {
+    if (kDot && tid == 0) R2.dotPartials[blockIdx.x] = 0.0;
     // ===== halo pusher CTA: all threads =====
     const HaloExchangeDev& H = F.H;
     const int pb = blockIdx.x - nAx;
@@ -330,6 +332,7 @@ __global__ void __launch_bounds__(NGROUPS* Nq* Nq + 32, 1)
   const int tbase = S::rot(a, b) + Nq * b;
   const T lam0 = lambda0[0];
   const T lam1 = kPoisson ? T(0) : lambda1[0];
+  T dotAcc = T(0);  // kDot: this thread's share of q^T A q
 
   for (int i = g; i < myCount; i += NGROUPS) {
     const int s = i % NSTAGES;
@@ -397,9 +400,19 @@ __global__ void __launch_bounds__(NGROUPS* Nq* Nq + 32, 1)
       T Gqt = G02 * qr;
       Gqt += G12 * qs;
       Gqt += G22 * qt;
+      if constexpr (kDot) {
+        T e = qr * Gqr;
+        e += qs * Gqs;
+        e += qt * Gqt;
+        if constexpr (!kPoisson) e = lam0 * e + r_mass[k] * r_q[k];
+        dotAcc += e;
+      }
       sr[p] = lam0 * Gqr;
       ss[p] = lam0 * Gqs;
       r_qt[k] = lam0 * Gqt;
+      // kDot: keep ptxas from hoisting all 64 shared loads of this loop above the first FMA (it then spills)
+      if constexpr (kDot)
+        if (k == Nq / 2 - 1) __syncwarp();
     }
     // the stage is no longer needed: hand it back to the producer
     mbar_arrive(&empty[s]);
@@ -452,6 +465,19 @@ __global__ void __launch_bounds__(NGROUPS* Nq* Nq + 32, 1)
     if (haloElem && t == 0) atomicAdd(F.counter, 1ull);
   }
 
+  if constexpr (kDot) {
+    // fixed-order fold: lanes (shuffle tree) -> warps (ascending) -> one partial per CTA
+    double* s_dot = reinterpret_cast<double*>(empty + NSTAGES);
+    const double wsum = warp_sum(kPoisson ? (double)(lam0 * dotAcc) : (double)dotAcc);
+    if ((tid & 31) == 0) s_dot[tid >> 5] = wsum;
+    group_sync(14, nConsumers);
+    if (tid == 0) {
+      double tot = 0.0;
+      for (int w = 0; w < nConsumers / 32; ++w) tot += s_dot[w];
+      R2.dotPartials[blockIdx.x] = tot;
+    }
+  }
+
   if constexpr (kGs) {
     // ===== phase 2: mask + on-rank gather-scatter by the consumer threads of all axhelm CTAs =====
     const int nT = nAx * nConsumers;
@@ -473,17 +499,18 @@ __global__ void __launch_bounds__(NGROUPS* Nq* Nq + 32, 1)
   }
 }
 
-template <typename T, int Nq, int NGROUPS, int NSTAGES, bool kPoisson, bool kFused = false, bool kGs = false>
+template <typename T, int Nq, int NGROUPS, int NSTAGES, bool kPoisson, bool kFused = false, bool kGs = false,
+          bool kDot = false>
 static int launch_tma(dlong Nelements, const dlong* elementList, const T* ggeo, const T* D_host, const T* lambda0,
                       const T* lambda1, const T* q, T* Aq, cudaStream_t stream, const FusedHalo* fused = nullptr,
-                      FusedRows* rows = nullptr)
+                      FusedRows* rows = nullptr, AxDot* dot = nullptr)
 {
   constexpr int Np = Nq * Nq * Nq;
   constexpr int NG = kPoisson ? 6 : 7;
   using S = SlabT<T, Nq>;
   const size_t smem = ((size_t)NSTAGES * (NG + 1) * Np + (size_t)NGROUPS * 3 * S::size) * sizeof(T) +
                       2 * NSTAGES * sizeof(uint64_t) + 128;
-  auto kern = ax_tma_kernel<T, Nq, NGROUPS, NSTAGES, kPoisson, kFused, kGs>;
+  auto kern = ax_tma_kernel<T, Nq, NGROUPS, NSTAGES, kPoisson, kFused, kGs, kDot>;
   static bool configured = false;
   if (!configured) {
     NRSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -501,6 +528,10 @@ static int launch_tma(dlong Nelements, const dlong* elementList, const T* ggeo, 
     R2.target += (unsigned long long)(kFused ? grid - F.nPush : grid);  // every axhelm CTA arrives once
     rows->target = R2.target;
   }
+  if (kDot) {
+    R2.dotPartials = dot->partials;
+    dot->n = grid;
+  }
   // (Launching this kernel as a programmatic dependent launch, with the first geometric-factor slabs requested
   // before griddepcontrol.wait, was measured slower: 28-29 us per launch with the attribute, 31-33 us without it,
   // against 26.7 us for the plain launch -- the wait itself resolves late.)
@@ -513,7 +544,7 @@ static int launch_tma(dlong Nelements, const dlong* elementList, const T* ggeo, 
 // variants 4..6 of the axhelm dispatch (Nq = 8, constant coefficients only)
 template <typename T>
 int ax_tma_launch(int Nq, int variant, dlong Nelements, const dlong* elementList, const T* ggeo, const T* D_host,
-                  const T* lambda0, const T* lambda1, int poisson, const T* q, T* Aq, cudaStream_t stream)
+                  const T* lambda0, const T* lambda1, int poisson, const T* q, T* Aq, cudaStream_t stream, AxDot* dot)
 {
   if (Nelements == 0) return NRSB_OK;
   if (Nq != 8) {
@@ -521,13 +552,23 @@ int ax_tma_launch(int Nq, int variant, dlong Nelements, const dlong* elementList
     return NRSB_ERR_INVALID;
   }
 #define NRSB_TMA(G, S_)                                                                                              \
-  return poisson ? launch_tma<T, 8, G, S_, true>(Nelements, elementList, ggeo, D_host, lambda0, lambda1, q, Aq, stream) \
-                 : launch_tma<T, 8, G, S_, false>(Nelements, elementList, ggeo, D_host, lambda0, lambda1, q, Aq, stream);
+  return poisson ? launch_tma<T, 8, G, S_, true>(Nelements, elementList, ggeo, D_host, lambda0, lambda1, q, Aq, stream, \
+                                                 nullptr, nullptr, dot)                                                 \
+                 : launch_tma<T, 8, G, S_, false>(Nelements, elementList, ggeo, D_host, lambda0, lambda1, q, Aq, stream, \
+                                                  nullptr, nullptr, dot);
   // NSTAGES must be a multiple of NGROUPS: group g then only ever touches stages == g (mod NGROUPS),
   // i.e. it owns a private sub-ring, and every mbarrier wait is at most one phase behind.
   if (sizeof(T) == 8) {
     if (variant == 4) { NRSB_TMA(4, 4) }
-    if (variant == 5) { NRSB_TMA(3, 6) }
+    if (variant == 5) {
+      if (dot && dot->partials)
+        return poisson ? launch_tma<T, 8, 3, 6, true, false, false, true>(Nelements, elementList, ggeo, D_host, lambda0,
+                                                                          lambda1, q, Aq, stream, nullptr, nullptr, dot)
+                       : launch_tma<T, 8, 3, 6, false, false, false, true>(Nelements, elementList, ggeo, D_host,
+                                                                           lambda0, lambda1, q, Aq, stream, nullptr,
+                                                                           nullptr, dot);
+      NRSB_TMA(3, 6)
+    }
     NRSB_TMA(5, 5)
   } else {
     if (variant == 4) { NRSB_TMA(4, 8) }
@@ -541,7 +582,7 @@ int ax_tma_launch(int Nq, int variant, dlong Nelements, const dlong* elementList
 template <typename T>
 int ax_tma_fused_launch(int Nq, int variant, dlong Nelements, const dlong* elementList, const T* ggeo, const T* D_host,
                         const T* lambda0, const T* lambda1, int poisson, const T* q, T* Aq, const FusedHalo& F,
-                        cudaStream_t stream)
+                        cudaStream_t stream, AxDot* dot)
 {
   if (Nelements == 0) return NRSB_OK;
   if (Nq != 8) {
@@ -551,10 +592,17 @@ int ax_tma_fused_launch(int Nq, int variant, dlong Nelements, const dlong* eleme
   (void)variant;
 #define NRSB_TMAF(G, S_)                                                                                      \
   return poisson ? launch_tma<T, 8, G, S_, true, true>(Nelements, elementList, ggeo, D_host, lambda0, lambda1, q, \
-                                                       Aq, stream, &F)                                         \
+                                                       Aq, stream, &F, nullptr, dot)                           \
                  : launch_tma<T, 8, G, S_, false, true>(Nelements, elementList, ggeo, D_host, lambda0, lambda1, q, \
-                                                        Aq, stream, &F);
-  if (sizeof(T) == 8) { NRSB_TMAF(3, 6) }
+                                                        Aq, stream, &F, nullptr, dot);
+  if (sizeof(T) == 8) {
+    if (dot && dot->partials)
+      return poisson ? launch_tma<T, 8, 3, 6, true, true, false, true>(Nelements, elementList, ggeo, D_host, lambda0,
+                                                                       lambda1, q, Aq, stream, &F, nullptr, dot)
+                     : launch_tma<T, 8, 3, 6, false, true, false, true>(Nelements, elementList, ggeo, D_host, lambda0,
+                                                                        lambda1, q, Aq, stream, &F, nullptr, dot);
+    NRSB_TMAF(3, 6)
+  }
   NRSB_TMAF(6, 12)
 #undef NRSB_TMAF
 }
@@ -563,7 +611,7 @@ int ax_tma_fused_launch(int Nq, int variant, dlong Nelements, const dlong* eleme
 template <typename T>
 int ax_tma_gs_launch(int Nq, dlong Nelements, const dlong* elementList, const T* ggeo, const T* D_host,
                      const T* lambda0, const T* lambda1, int poisson, const T* q, T* Aq, const FusedHalo* F,
-                     FusedRows* rows, cudaStream_t stream)
+                     FusedRows* rows, cudaStream_t stream, AxDot* dot)
 {
   if (Nelements == 0) return NRSB_OK;
   if (Nq != 8) {
@@ -572,9 +620,9 @@ int ax_tma_gs_launch(int Nq, dlong Nelements, const dlong* elementList, const T*
   }
 #define NRSB_TMAG(G_, S_, FUSED)                                                                                   \
   return poisson ? launch_tma<T, 8, G_, S_, true, FUSED, true>(Nelements, elementList, ggeo, D_host, lambda0, lambda1, \
-                                                              q, Aq, stream, F, rows)                                \
+                                                              q, Aq, stream, F, rows, dot)                           \
                  : launch_tma<T, 8, G_, S_, false, FUSED, true>(Nelements, elementList, ggeo, D_host, lambda0,       \
-                                                               lambda1, q, Aq, stream, F, rows);
+                                                               lambda1, q, Aq, stream, F, rows, dot);
   if (F) {
     if (sizeof(T) == 8) { NRSB_TMAG(3, 6, true) }
     NRSB_TMAG(6, 12, true)
@@ -585,18 +633,20 @@ int ax_tma_gs_launch(int Nq, dlong Nelements, const dlong* elementList, const T*
 }
 template int ax_tma_gs_launch<double>(int, dlong, const dlong*, const double*, const double*, const double*,
                                       const double*, int, const double*, double*, const FusedHalo*, FusedRows*,
-                                      cudaStream_t);
+                                      cudaStream_t, AxDot*);
 template int ax_tma_gs_launch<float>(int, dlong, const dlong*, const float*, const float*, const float*, const float*,
-                                     int, const float*, float*, const FusedHalo*, FusedRows*, cudaStream_t);
+                                     int, const float*, float*, const FusedHalo*, FusedRows*, cudaStream_t, AxDot*);
 
 template int ax_tma_fused_launch<double>(int, int, dlong, const dlong*, const double*, const double*, const double*,
-                                         const double*, int, const double*, double*, const FusedHalo&, cudaStream_t);
+                                         const double*, int, const double*, double*, const FusedHalo&, cudaStream_t,
+                                         AxDot*);
 template int ax_tma_fused_launch<float>(int, int, dlong, const dlong*, const float*, const float*, const float*,
-                                        const float*, int, const float*, float*, const FusedHalo&, cudaStream_t);
+                                        const float*, int, const float*, float*, const FusedHalo&, cudaStream_t,
+                                        AxDot*);
 
 template int ax_tma_launch<double>(int, int, dlong, const dlong*, const double*, const double*, const double*,
-                                   const double*, int, const double*, double*, cudaStream_t);
+                                   const double*, int, const double*, double*, cudaStream_t, AxDot*);
 template int ax_tma_launch<float>(int, int, dlong, const dlong*, const float*, const float*, const float*,
-                                  const float*, int, const float*, float*, cudaStream_t);
+                                  const float*, int, const float*, float*, cudaStream_t, AxDot*);
 
 }  // namespace nrsb

@@ -144,6 +144,22 @@ struct prec_traits<float> {
 };
 
 template <typename T>
+static int ellipticAxDot(elliptic_t* elliptic, dlong NelementsList, const dlong* o_elementList, const T* o_q, T* o_Aq,
+                         AxDot* dot)
+{
+  if (dot) dot->n = 0;
+  if (NelementsList == 0) return NRSB_OK;
+  mesh_t* mesh = elliptic->mesh;
+  using P = prec_traits<T>;
+  NRSB_REQUIRE(P::ggeo(mesh) != nullptr, "geometric factors of the requested precision are not resident");
+  int variant = elliptic->ax_variant[P::idx];
+  if (variant < 0) variant = ax_default_variant(mesh->Nq, (int)sizeof(T));
+  return ax_launch<T>(mesh->Nq, variant, NelementsList, elliptic->loffset, o_elementList, P::ggeo(mesh), P::D(mesh),
+                      P::lambda0(elliptic), P::lambda1(elliptic), elliptic->poisson ? 1 : 0, 0, o_q, o_Aq,
+                      elliptic->stream, dot);
+}
+
+template <typename T>
 int ellipticAx(elliptic_t* elliptic, dlong NelementsList, const dlong* o_elementList, const T* o_q, T* o_Aq)
 {
   if (NelementsList == 0) return NRSB_OK;
@@ -171,8 +187,9 @@ template int ellipticApplyMask<float>(elliptic_t*, float*);
 // their partial sums are pushed to the neighbours (oogs::start), the interior elements follow while
 // the NVLink stores are in flight, and oogs::finish folds everything (and the mask) in one kernel.
 template <typename T>
-int ellipticOperator(elliptic_t* elliptic, const T* o_q, T* o_Aq, bool masked)
+int ellipticOperator(elliptic_t* elliptic, const T* o_q, T* o_Aq, bool masked, AxDot* dot)
 {
+  if (dot) dot->n = 0;
   mesh_t* mesh = elliptic->mesh;
   oogs_t* oogs = elliptic->oogs.get();
   int rc;
@@ -197,7 +214,7 @@ int ellipticOperator(elliptic_t* elliptic, const T* o_q, T* o_Aq, bool masked)
     // single rank: the whole operator (Ax, mask, gather-scatter) is ONE launch
     rc = ax_tma_gs_launch<T>(mesh->Nq, mesh->Nelements, mesh->o_elementList.p, P::ggeo(mesh), P::D(mesh),
                              P::lambda0(elliptic), P::lambda1(elliptic), elliptic->poisson ? 1 : 0, o_q, o_Aq, nullptr,
-                             &FR, elliptic->stream);
+                             &FR, elliptic->stream, dot);
     elliptic->fusedArriveTarget = FR.target;
     return rc;
   }
@@ -222,7 +239,7 @@ int ellipticOperator(elliptic_t* elliptic, const T* o_q, T* o_Aq, bool masked)
     }
     if ((rc = ax_tma_fused_launch<T>(mesh->Nq, 5, mesh->Nelements, mesh->o_haloFirstElementList.p, P::ggeo(mesh),
                                      P::D(mesh), P::lambda0(elliptic), P::lambda1(elliptic), elliptic->poisson ? 1 : 0,
-                                     o_q, o_Aq, F, elliptic->stream)))
+                                     o_q, o_Aq, F, elliptic->stream, dot)))
       return rc;
     if (timing) cudaEventRecord(ev[3 * nrec + 1], elliptic->stream);
     rc = oogs->finish<T>(o_Aq, 1, elliptic->fieldOffset, gs_op::add, nm, elliptic->o_maskIds.p, elliptic->stream);
@@ -257,7 +274,7 @@ int ellipticOperator(elliptic_t* elliptic, const T* o_q, T* o_Aq, bool masked)
     return oogs->finish<T>(o_Aq, elliptic->Nfields, elliptic->fieldOffset, gs_op::add,
                            masked ? elliptic->NmaskedLocal : 0, elliptic->o_maskIdsLocal.p, elliptic->stream);
   }
-  if ((rc = ellipticAx<T>(elliptic, mesh->Nelements, mesh->o_elementList.p, o_q, o_Aq))) return rc;
+  if ((rc = ellipticAxDot<T>(elliptic, mesh->Nelements, mesh->o_elementList.p, o_q, o_Aq, dot))) return rc;
   if (oogs->ogs->NhaloGather) {
     // halo rows are packed from masked values: mask first
     if (nm)
@@ -268,8 +285,8 @@ int ellipticOperator(elliptic_t* elliptic, const T* o_q, T* o_Aq, bool masked)
   return oogs->startFinish<T>(o_Aq, elliptic->Nfields, elliptic->fieldOffset, gs_op::add, nm, elliptic->o_maskIds.p,
                               elliptic->stream);
 }
-template int ellipticOperator<double>(elliptic_t*, const double*, double*, bool);
-template int ellipticOperator<float>(elliptic_t*, const float*, float*, bool);
+template int ellipticOperator<double>(elliptic_t*, const double*, double*, bool, AxDot*);
+template int ellipticOperator<float>(elliptic_t*, const float*, float*, bool, AxDot*);
 
 int ellipticZeroMean(elliptic_t* elliptic, double* o_q)
 {
@@ -403,6 +420,7 @@ int ellipticSolveSetup(elliptic_t* elliptic)
   // 2048-threads-per-SM kernel does in 12.5 us (both bound by LSU wavefronts of the scattered 8-byte accesses),
   // 42.0 vs 39.4 us per operator at E=4096: off unless asked for
   elliptic->fusedGsAx = options.compareArgs("FUSED GS AX", "TRUE") || getenv("NRSB_FUSED_GS") != nullptr;
+  elliptic->fusedDotAx = !options.compareArgs("FUSED DOT AX", "FALSE") && getenv("NRSB_NO_FUSED_DOT") == nullptr;
   elliptic->overlap = elliptic->ogs->NhaloGather > 0 && !options.compareArgs("ENABLE GS COMM OVERLAP", "FALSE") &&
                       mesh->NlocalGatherElements > 0;
 
@@ -520,6 +538,8 @@ int pcg(elliptic_t* elliptic, double* o_r, double* o_x, double tol, int MAXIT, d
   interval = std::max(1, interval);
   if (elliptic->o_resHist.n < (size_t)MAXIT + 1)
     if ((rc = elliptic->o_resHist.alloc((size_t)MAXIT + 1))) return rc;
+  if (!elliptic->o_dotPartials.p)
+    if ((rc = elliptic->o_dotPartials.alloc(kNumSMs))) return rc;
   {
     const double init[3] = {0.0, 0.0, rdotr};
     NRSB_CUDA(cudaMemcpyAsync(S + S_DONE, init, sizeof(init), cudaMemcpyHostToDevice, st));
@@ -559,10 +579,17 @@ int pcg(elliptic_t* elliptic, double* o_r, double* o_x, double tol, int MAXIT, d
     }
     // p = z + beta p
     if ((rc = axpby_launch<double>(N, DevScalar::host(1.0), o_z, beta, o_p, st))) return rc;
-    if ((rc = ellipticOperator<double>(elliptic, o_p, o_Ap))) return rc;
-    // pAp and alpha = rdotz1 / (pAp + 1e-300) in one launch
-    if ((rc = wdot_ratio_launch(N, o_weight, o_p, o_Ap, S + S_PAP, S + S_RDOTZ, 1e-300, S + S_ALPHA, elliptic->ws, st)))
-      return rc;
+    AxDot dot;
+    dot.partials = elliptic->o_dotPartials.p;
+    if ((rc = ellipticOperator<double>(elliptic, o_p, o_Ap, true, elliptic->fusedDotAx ? &dot : nullptr))) return rc;
+    // pAp and alpha = rdotz1 / (pAp + 1e-300) in one launch: either the fold of the per-CTA values of p^T A_L p
+    // that the axhelm launch left behind (p is continuous and masked, so this IS sum invDegree p Ap), or the
+    // reference's separate pass over p and Ap (PCG.cpp:150-157)
+    if (dot.n > 0)
+      rc = sum_ratio_launch(dot.n, dot.partials, S + S_PAP, S + S_RDOTZ, 1e-300, S + S_ALPHA, elliptic->ws, st);
+    else
+      rc = wdot_ratio_launch(N, o_weight, o_p, o_Ap, S + S_PAP, S + S_RDOTZ, 1e-300, S + S_ALPHA, elliptic->ws, st);
+    if (rc) return rc;
     DevScalar alpha = DevScalar::ratio(S + S_ALPHA, nullptr);
     // x += alpha p ; r -= alpha Ap ; rdotr = sqrt(sum w r^2 * factor) ; history ; convergence flag  (one kernel)
     ctl.iter = iter;

@@ -91,6 +91,12 @@ struct FusedRows {
   GsRowsDev R;
   unsigned long long* arrive = nullptr;  // monotone arrival counter of the axhelm CTAs
   unsigned long long target = 0;         // its value once every axhelm CTA of this launch has arrived
+  // (any ax_tma launch) when set: CTA b stores  sum over its elements of  q_e^T A_e q_e  (energy form
+  // lam0 * grad q . G grad q [+ lam1 * GwJ q^2], evaluated where the kernel already holds those factors) to
+  // dotPartials[b].  For a continuous q (PCG's p) the sum over CTAs is  q^T Q^T A_L Q q = the weighted inner
+  // product  sum invDegree * q * (Q Q^T A_L q)  that PCG.cpp:150-157 computes with a separate pass after the
+  // gather-scatter.
+  double* dotPartials = nullptr;
 };
 
 template <typename T>

@@ -315,6 +315,9 @@ class elliptic_t {
   // mask + on-rank gather-scatter as phase 2 of the axhelm launch when Nq == 8 (struct FusedRows, gs.hpp)
   bool fusedGsAx = false;
   dbuf<unsigned long long> fusedArrive;  // arrival counter of the axhelm CTAs, never reset
+  // PCG: p^T A p from the axhelm launch (energy form) instead of a separate weighted-inner-product pass
+  bool fusedDotAx = true;
+  dbuf<double> o_dotPartials;
   unsigned long long fusedArriveTarget = 0;
   dlong Nmasked = 0, NmaskedLocal = 0, NmaskedGlobal = 0;
   dbuf<dlong> o_maskIds, o_maskIdsLocal, o_maskIdsGlobal;
@@ -364,8 +367,10 @@ int ellipticSolveSetup(elliptic_t* elliptic);
 int ellipticSolve(elliptic_t* elliptic, double* o_r, double* o_x);
 template <typename T>
 int ellipticAx(elliptic_t* elliptic, dlong NelementsList, const dlong* o_elementList, const T* o_q, T* o_Aq);
+// dot != nullptr: ask the axhelm launch for q^T A q (per-CTA partials, kernels.hpp AxDot); dot->n == 0 on return
+// means the launch path taken could not provide it
 template <typename T>
-int ellipticOperator(elliptic_t* elliptic, const T* o_q, T* o_Aq, bool masked = true);
+int ellipticOperator(elliptic_t* elliptic, const T* o_q, T* o_Aq, bool masked = true, AxDot* dot = nullptr);
 template <typename T>
 int ellipticApplyMask(elliptic_t* elliptic, T* o_x);
 int ellipticZeroMean(elliptic_t* elliptic, double* o_q);

@@ -5,22 +5,28 @@
 namespace nrsb {
 
 // axhelm.cu
+// request for q^T A q from the axhelm launch itself (persistent TMA kernels only): `partials` receives one value per
+// CTA, `n` is set to their number; a launcher that cannot honour it sets n = 0 (the caller then uses a separate pass)
+struct AxDot {
+  double* partials = nullptr;
+  int n = 0;
+};
 template <typename T>
 int ax_launch(int Nq, int variant, dlong Nelements, dlong loffset, const dlong* elementList, const T* ggeo,
               const T* D_host, const T* lambda0, const T* lambda1, int poisson, int lambdaField, const T* q, T* Aq,
-              cudaStream_t stream);
+              cudaStream_t stream, AxDot* dot = nullptr);
 int ax_default_variant(int Nq, int precision);
 struct FusedHalo;
 template <typename T>
 int ax_tma_fused_launch(int Nq, int variant, dlong Nelements, const dlong* elementList, const T* ggeo, const T* D_host,
                         const T* lambda0, const T* lambda1, int poisson, const T* q, T* Aq, const FusedHalo& F,
-                        cudaStream_t stream);
+                        cudaStream_t stream, AxDot* dot = nullptr);
 
 struct FusedRows;
 template <typename T>
 int ax_tma_gs_launch(int Nq, dlong Nelements, const dlong* elementList, const T* ggeo, const T* D_host,
                      const T* lambda0, const T* lambda1, int poisson, const T* q, T* Aq, const FusedHalo* F,
-                     FusedRows* rows, cudaStream_t stream);
+                     FusedRows* rows, cudaStream_t stream, AxDot* dot = nullptr);
 
 // fdm.cu
 int fused_fdm_launch(int Nq, int restrict_, dlong Nelements, const dlong* elementList, float* Su, const float* Sx,

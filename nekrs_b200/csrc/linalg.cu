@@ -295,6 +295,14 @@ int wdot_ratio_launch(long N, const double* w, const double* x, const double* y,
       RatioPost{num, shift, alpha});
 }
 
+// out = sum_i v[i] (fixed order), alpha = num / (out + shift): folds per-CTA partials left by another kernel
+int sum_ratio_launch(long n, const double* v, double* out, const double* num, double shift, double* alpha,
+                     const ReduceWs& ws, cudaStream_t s)
+{
+  return reduce_launch<1>(
+      n, [=] __device__(long i, double* acc) { acc[0] += v[i]; }, 1, out, ws, s, RatioPost{num, shift, alpha});
+}
+
 int gram_schmidt_launch(long N, long offset, int gmresSize, const double* w, const double* y, const double* V,
                         double* wv, double* out, const ReduceWs& ws, cudaStream_t s)
 {

@@ -108,6 +108,8 @@ struct PcgControl {
 int update_pcg_ctl_launch(long N, const double* w, const double* Ap, const double* p, DevScalar alpha, double* r,
                           double* x, double* out, PcgControl c, const ReduceWs& ws, cudaStream_t s);
 // out = sum w x y ; alpha[0] = num[0] / (out + shift)   (pAp and the step length in one launch)
+int sum_ratio_launch(long n, const double* v, double* out, const double* num, double shift, double* alpha,
+                     const ReduceWs& ws, cudaStream_t s);
 int wdot_ratio_launch(long N, const double* w, const double* x, const double* y, double* out, const double* num,
                       double shift, double* alpha, const ReduceWs& ws, cudaStream_t s);
 
