@@ -28,8 +28,8 @@ namespace nrsb {
 // local index, as the reference's CSR loop does (bit-identical sums).
 // The kernel is launched as a programmatic dependent launch: blocks may become resident while the producer
 // (axhelm) is still running, fetch their index entries, and sleep in pdl_wait() until its stores are visible.
-template <typename T, int kRPT>
-__global__ void __launch_bounds__(kBlockSize)
+template <typename T, int kRPT, int kBS>
+__global__ void __launch_bounds__(kBS, kRPT == 1 ? 2048 / kBS : 1)  // 1 row per thread: 32 registers, 2048 threads per SM
     gs_rows_kernel(const GsRowsDev R, const int Nfields, const dlong stride, T* __restrict__ q)
 {
   (void)Nfields;
@@ -77,10 +77,18 @@ int gs_rows_launch(const GsRowsDev& R, int Nfields, dlong stride, T* q, cudaStre
   const long total = (long)R.nPairs + R.nQuads + R.nOcts + R.nGen + R.nMasked;
   if (total == 0 || Nfields == 0) return NRSB_OK;
   const int rpt = gs_rows_per_thread();
-  const long perBlock = (long)kBlockSize * rpt;
+  static const int bs = [] {
+    const char* e = getenv("NRSB_GS_BS");
+    const int v = e ? atoi(e) : 128;  // measured (tools/gs_timing.py): 64: 12.35, 128: 11.7-12.3, 256: 12.35, 512: 13.7, 1024: 17.4 us
+    return (v == 64 || v == 256 || v == 512 || v == 1024) ? v : 128;
+  }();
+  const long perBlock = (long)bs * rpt;
   dim3 grid((unsigned)((total + perBlock - 1) / perBlock), Nfields);
-  auto kern = rpt == 1 ? gs_rows_kernel<T, 1> : (rpt == 2 ? gs_rows_kernel<T, 2> : gs_rows_kernel<T, 4>);
-  NRSB_CUDA(launch_pdl_consumer(kern, grid, dim3(kBlockSize), 0, stream, R, Nfields, stride, q));
+  auto kern = rpt == 1 ? (bs == 64 ? gs_rows_kernel<T, 1, 64> : bs == 128 ? gs_rows_kernel<T, 1, 128>
+                                    : (bs == 512 ? gs_rows_kernel<T, 1, 512>
+                                                 : (bs == 1024 ? gs_rows_kernel<T, 1, 1024> : gs_rows_kernel<T, 1, 256>)))
+                       : (rpt == 2 ? gs_rows_kernel<T, 2, 256> : gs_rows_kernel<T, 4, 256>);
+  NRSB_CUDA(launch_pdl_consumer(kern, grid, dim3(rpt == 1 ? bs : 256), 0, stream, R, Nfields, stride, q));
   return NRSB_OK;
 }
 template int gs_rows_launch<double>(const GsRowsDev&, int, dlong, double*, cudaStream_t);
