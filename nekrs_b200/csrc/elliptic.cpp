@@ -550,20 +550,21 @@ int pcg(elliptic_t* elliptic, double* o_r, double* o_x, double tol, int MAXIT, d
   ctl.hist = elliptic->o_resHist.p;
   ctl.factor = elliptic->resNormFactor;
   ctl.tol = tol;
+  ctl.rdotz = S + S_RDOTZ;
+  ctl.rdotzOld = S + S_RDOTZ_OLD;
+  ctl.normIsRdotz = precond ? 0 : 1;
+  if (!precond)  // first iteration: rdotz1 = rdotr (the norm on entry)
+    NRSB_CUDA(cudaMemcpyAsync(S + S_RDOTZ, S + S_RDOTR, sizeof(double), cudaMemcpyDeviceToDevice, st));
 
   int iter = 0;
   bool done = false;
   do {
     iter++;
-    // rdotz2 = rdotz1
-    NRSB_CUDA(cudaMemcpyAsync(S + S_RDOTZ_OLD, S + S_RDOTZ, sizeof(double), cudaMemcpyDeviceToDevice, st));
+    // rdotz2 = rdotz1 was done by the last block of the previous iteration's update kernel (PcgControl), and so
+    // was, without preconditioner, rdotz1 = rdotr: the residual NORM of the previous iteration
     if (precond) {
       if ((rc = ellipticPreconditioner(elliptic, o_r, o_z))) return rc;
       if ((rc = wdot_launch<double>(N, o_weight, o_r, o_z, S + S_RDOTZ, elliptic->ws, st))) return rc;
-    } else {
-      // rdotz1 = rdotr: the residual NORM of the previous iteration (device copy kept by PcgCtlPost)
-      NRSB_CUDA(cudaMemcpyAsync(S + S_RDOTZ, iter == 1 ? S + S_RDOTR : S + S_CURNORM, sizeof(double),
-                                cudaMemcpyDeviceToDevice, st));
     }
     DevScalar beta = DevScalar::host(0.0);
     if (iter > 1) {

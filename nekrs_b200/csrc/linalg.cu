@@ -258,6 +258,8 @@ struct PcgCtlPost {
     const double rd = sqrt(tot[0] * c.factor);
     c.ctl[2] = rd;
     c.hist[c.iter - 1] = rd;
+    if (c.rdotzOld) c.rdotzOld[0] = c.rdotz[0];
+    if (c.normIsRdotz) c.rdotz[0] = rd;
     if (!(rd > c.tol)) {  // also taken for NaN, like the reference's loop condition
       c.ctl[0] = 1.0;
       c.ctl[1] = (double)c.iter;

@@ -104,6 +104,12 @@ struct PcgControl {
   double* hist = nullptr;
   double factor = 1.0, tol = 0.0;
   int iter = 0;
+  // scalar hand-over to the next iteration, done by the last block instead of two 8-byte device copies:
+  // rdotzOld = rdotz ("rdotz2 = rdotz1", PCG.cpp:121) and, without preconditioner, rdotz = the new residual
+  // norm ("rdotz1 = rdotr", PCG.cpp:131)
+  double* rdotz = nullptr;
+  double* rdotzOld = nullptr;
+  int normIsRdotz = 0;
 };
 int update_pcg_ctl_launch(long N, const double* w, const double* Ap, const double* p, DevScalar alpha, double* r,
                           double* x, double* out, PcgControl c, const ReduceWs& ws, cudaStream_t s);
