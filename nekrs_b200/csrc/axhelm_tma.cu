@@ -78,6 +78,12 @@ __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long
   asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void group_sync(int id, int nthreads)
 {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -284,6 +290,8 @@ __global__ void __launch_bounds__(NGROUPS* Nq* Nq + 32, 1)
     const int e00 = pb * blockDim.x + tid;
     HaloSendBatch<16> first;
     halo_pack_load<16>(H, e00, estride, first);
+    const bool stamp = F.stamps && pb == 0 && tid == 0;
+    if (stamp) F.stamps[0] = globaltimer_ns();
     if (tid == 0) {
       const long long t0 = clock64();
       while (ld_acquire_u64(F.counter) < F.target) {
@@ -292,16 +300,22 @@ __global__ void __launch_bounds__(NGROUPS* Nq* Nq + 32, 1)
       }
     }
     __syncthreads();
+    if (stamp) F.stamps[1] = globaltimer_ns();
     halo_pack_store<T, 16, true>(H, gs_op::add, Aq, (T*)F.partial, e00, estride, first);
     for (int e0 = e00 + 16 * estride; e0 < H.nSend; e0 += 8 * estride)
       halo_pack_flat<T, 8, true>(H, gs_op::add, Aq, (T*)F.partial, e0, estride);
+    if (stamp) F.stamps[2] = globaltimer_ns();
     __threadfence_system();
     __syncthreads();
+    if (stamp) F.stamps[3] = globaltimer_ns();
     // this pusher's rows are out: raise ITS flag slot at every peer (receivers wait for all kFlagSlots slots)
-    for (int p = tid; p < H.nPeers; p += blockDim.x) {
-      volatile unsigned long long* f = H.peerFlags[p] + (size_t)H.myRank * kFlagSlots + pb;
+    for (int i = tid; i < H.nPeers * kFlagSlots; i += blockDim.x) {
+      const int p = i / kFlagSlots, slot = i % kFlagSlots;
+      if (slot % F.nPush != pb) continue;
+      volatile unsigned long long* f = H.peerFlags[p] + (size_t)H.myRank * kFlagSlots + slot;
       *f = H.epoch;
     }
+    if (stamp) F.stamps[4] = globaltimer_ns();
     return;
   }
   if (tid >= nConsumers) {
@@ -460,11 +474,18 @@ __global__ void __launch_bounds__(NGROUPS* Nq* Nq + 32, 1)
       Ae[k * Nq2] = v;
     }
     const bool haloElem = kFused && (blockIdx.x + (dlong)i * nAx < F.NhaloElements);
-    if (haloElem) __threadfence();
     group_sync(1 + g, Nq2);  // su/ss are rewritten by the next element of this group
-    if (haloElem && t == 0) atomicAdd(F.counter, 1ull);
+    if (haloElem && t == 0) {
+      // the group's stores are ordered before this point by the barrier; one fence (cumulative) publishes them
+      __threadfence();
+      atomicAdd(F.counter, 1ull);
+    }
   }
 
+  if (kFused && F.stamps && tid == 0) {
+    if (blockIdx.x == 0) F.stamps[8] = globaltimer_ns();
+    if ((int)blockIdx.x == nAx - 1) F.stamps[9] = globaltimer_ns();
+  }
   if constexpr (kDot) {
     // fixed-order fold: lanes (shuffle tree) -> warps (ascending) -> one partial per CTA
     double* s_dot = reinterpret_cast<double*>(empty + NSTAGES);

@@ -236,6 +236,12 @@ int ellipticOperator(elliptic_t* elliptic, const T* o_q, T* o_Aq, bool masked, A
         for (auto& x : ev) cudaEventCreate(&x);
       }
       cudaEventRecord(ev[3 * nrec], elliptic->stream);
+      static unsigned long long* d_stamps = nullptr;
+      if (!d_stamps) {
+        cudaMalloc((void**)&d_stamps, 16 * sizeof(unsigned long long));
+        cudaMemset(d_stamps, 0, 16 * sizeof(unsigned long long));
+      }
+      F.stamps = d_stamps;
     }
     if ((rc = ax_tma_fused_launch<T>(mesh->Nq, 5, mesh->Nelements, mesh->o_haloFirstElementList.p, P::ggeo(mesh),
                                      P::D(mesh), P::lambda0(elliptic), P::lambda1(elliptic), elliptic->poisson ? 1 : 0,
@@ -257,6 +263,13 @@ int ellipticOperator(elliptic_t* elliptic, const T* o_q, T* o_Aq, bool masked, A
         }
         fprintf(stderr, "[rank %d] fused operator: Ax+push %.2f us, finish %.2f us (mean of %d, pipelined)\n",
                 mesh->comm ? mesh->comm->rank : 0, sa / kRing * 1e3, sb / kRing * 1e3, kRing);
+        unsigned long long h[16];
+        cudaMemcpy(h, F.stamps, sizeof(h), cudaMemcpyDeviceToHost);
+        fprintf(stderr,
+                "[rank %d]   last launch, ns after pusher start: halo elements stored %lld, pushed %lld, fenced %lld, "
+                "flags %lld, axhelm CTA 0 done %lld, last axhelm CTA done %lld\n",
+                mesh->comm ? mesh->comm->rank : 0, (long long)(h[1] - h[0]), (long long)(h[2] - h[0]),
+                (long long)(h[3] - h[0]), (long long)(h[4] - h[0]), (long long)(h[8] - h[0]), (long long)(h[9] - h[0]));
         nrec = 0;
       }
     }

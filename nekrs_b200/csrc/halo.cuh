@@ -6,7 +6,7 @@
 
 namespace nrsb {
 
-constexpr int kFlagSlots = 8;    // arrival flags per sender: one per pusher CTA of the fused launch
+constexpr int kFlagSlots = 16;   // arrival flags per sender: pusher CTA pb of the fused launch raises slots pb, pb + nPush, ...
 constexpr int kInlinePeers = 8;  // peer window pointers carried in the kernel parameters (no dependent load)
 
 struct HaloExchangeDev {
@@ -19,8 +19,10 @@ struct HaloExchangeDev {
   // flat send table for one field (k = 1): one entry per (row, destination), sorted by row.
   //   sendFlat[e] = {id0, id1 (-1: single local copy), peer | kSendFirst | kSendSlow, absolute slot in the peer window}
   //   (kSendSlow: more than two local copies, id0 = row index -> CSR walk);  sendRow[e] = row
+  //   kSendQuad: three or four local copies, the third and fourth id in sendExtra[e] (element corners on a rank face)
   int nSend;
   const int4* sendFlat;
+  const int2* sendExtra;
   const int* sendRow;
   // flat receive table for one field: recvFlat[row] = {absolute slot a, absolute slot b, position of the own
   // partial among the contributions (ascending rank), number of contributions}; valid when that number <= 3,
@@ -76,12 +78,14 @@ __device__ __forceinline__ void halo_pack_row(const HaloExchangeDev& H, const in
 
 constexpr int kSendFirst = 1 << 16;  // first destination of its row: also stores partial[row]
 constexpr int kSendSlow = 1 << 17;
+constexpr int kSendQuad = 1 << 18;
 
 // kB send entries per thread in two steps, so that a caller can issue the index loads BEFORE the data is
 // ready (they do not depend on it) and keep only  value load -> NVLink store  on the critical path.
 template <int kB>
 struct HaloSendBatch {
   int4 s[kB];
+  int2 x[kB];
   int row[kB];
 };
 
@@ -93,9 +97,11 @@ __device__ __forceinline__ void halo_pack_load(const HaloExchangeDev& H, const i
   for (int j = 0; j < kB; ++j) {
     const int e = e0 + j * estride;
     b.s[j] = make_int4(-1, -1, 0, 0);
+    b.x[j] = make_int2(-1, -1);
     b.row[j] = 0;
     if (e < H.nSend) {
       b.s[j] = H.sendFlat[e];
+      b.x[j] = H.sendExtra[e];
       b.row[j] = H.sendRow[e];
     }
   }
@@ -119,7 +125,12 @@ __device__ __forceinline__ void halo_pack_store(const HaloExchangeDev& H, const 
         val[j] = a;
       } else {
         const T a = ld(b.s[j].x);
-        val[j] = (b.s[j].y >= 0) ? gs_combine(a, ld(b.s[j].y), op) : a;
+        T sum = (b.s[j].y >= 0) ? gs_combine(a, ld(b.s[j].y), op) : a;
+        if (b.s[j].z & kSendQuad) {
+          sum = gs_combine(sum, ld(b.x[j].x), op);
+          if (b.x[j].y >= 0) sum = gs_combine(sum, ld(b.x[j].y), op);
+        }
+        val[j] = sum;
       }
     }
   }
@@ -151,6 +162,9 @@ struct FusedHalo {
   unsigned long long target = 0;          // value of *counter once this launch's halo elements are all stored
   void* partial = nullptr;
   dlong stride = 0;
+  // developer aid (NRSB_OP_TIMING): globaltimer stamps, [0..4] pusher 0 (start, halo elements stored, pushed,
+  // fenced, flags raised), [8] first / [9] last axhelm CTA done
+  unsigned long long* stamps = nullptr;
 };
 
 }  // namespace nrsb

@@ -73,6 +73,7 @@ template struct dbuf<unsigned long long>;
 template struct dbuf<double*>;
 template struct dbuf<float*>;
 template struct dbuf<int4>;
+template struct dbuf<int2>;
 template struct dbuf<unsigned long long*>;
 template struct dbuf<void*>;
 template struct dbuf<long>;

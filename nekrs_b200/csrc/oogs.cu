@@ -20,6 +20,7 @@
 // ahead of a neighbour because finish(e) needs the neighbour's flag e.
 #include <algorithm>
 #include <cstring>
+#include <cstdlib>
 #include <map>
 
 #include "halo.cuh"
@@ -119,9 +120,8 @@ __device__ __forceinline__ void unpack_rows_body(const HaloExchangeDev& H, const
   }
   // ---- halo rows: wait for every peer's epoch flag, then fold
   if (blockIdx.y != 0) return;  // halo blocks handle all fields themselves
-  if (threadIdx.x < H.nPeers * kFlagSlots) {
-    volatile unsigned long long* f =
-        H.myFlags + (size_t)H.peerRank[threadIdx.x / kFlagSlots] * kFlagSlots + threadIdx.x % kFlagSlots;
+  for (int i = threadIdx.x; i < H.nPeers * kFlagSlots; i += blockDim.x) {
+    volatile unsigned long long* f = H.myFlags + (size_t)H.peerRank[i / kFlagSlots] * kFlagSlots + i % kFlagSlots;
     while (*f < H.epoch) {
     }
   }
@@ -187,6 +187,7 @@ __global__ void __launch_bounds__(kBlockSize)
 struct oogs_dev_t {
   std::vector<void*> h_peerWindow[2];
   dbuf<int4> sendFlat, recvFlat, rowLocal;
+  dbuf<int2> sendExtra;
   dbuf<int> sendRow;
   dbuf<long> peerRemoteOffset, peerRecvOffset;
   dbuf<int> peerCount, peerRank;
@@ -333,6 +334,7 @@ int oogs_t::setup(ogs_t* ogs_, comm_t* comm_, int maxFields_)
   }
   {
     std::vector<int4> flat(sendPeer.size());
+    std::vector<int2> fextra(sendPeer.size(), make_int2(-1, -1));
     std::vector<int> frow(sendPeer.size());
     for (int r = 0; r < nRows; ++r) {
       const int c0 = ogs->haloGatherOffsets[r], c1 = ogs->haloGatherOffsets[r + 1];
@@ -341,7 +343,11 @@ int oogs_t::setup(ogs_t* ogs_, comm_t* comm_, int maxFields_)
         if (d == sendStarts[r]) code |= kSendFirst;
         int id0 = ogs->haloGatherIds[c0], id1 = -1;
         if (c1 - c0 == 2) id1 = ogs->haloGatherIds[c0 + 1];
-        if (c1 - c0 > 2) {
+        if (c1 - c0 == 3 || c1 - c0 == 4) {
+          code |= kSendQuad;
+          id1 = ogs->haloGatherIds[c0 + 1];
+          fextra[d] = make_int2(ogs->haloGatherIds[c0 + 2], c1 - c0 == 4 ? ogs->haloGatherIds[c0 + 3] : -1);
+        } else if (c1 - c0 > 4) {
           code |= kSendSlow;
           id0 = r;
         }
@@ -350,6 +356,7 @@ int oogs_t::setup(ogs_t* ogs_, comm_t* comm_, int maxFields_)
       }
     }
     if ((rc = dev->sendFlat.upload(flat))) return rc;
+    if ((rc = dev->sendExtra.upload(fextra))) return rc;
     if ((rc = dev->sendRow.upload(frow))) return rc;
     std::vector<int4> rflat(nRows), rloc(nRows);
     for (int r = 0; r < nRows; ++r) {
@@ -408,6 +415,7 @@ static HaloExchangeDev make_dev(oogs_t* o, oogs_dev_t* d, int parity)
   H.sendSlot = o->d_sendSlot.p;
   H.nSend = (int)d->sendFlat.n;
   H.sendFlat = d->sendFlat.p;
+  H.sendExtra = d->sendExtra.p;
   H.sendRow = d->sendRow.p;
   H.recvFlat = d->recvFlat.p;
   H.rowLocal = d->rowLocal.p;
@@ -436,7 +444,7 @@ int oogs_t::start(T* v, int k, dlong stride, gs_op op, cudaStream_t stream)
 {
   if (!ogs || ogs->NhaloGather == 0) return NRSB_OK;
   NRSB_REQUIRE(k <= maxFields, "oogs::start: more fields than the handle was set up for");
-  NRSB_REQUIRE((int)peers.size() * kFlagSlots <= kBlockSize, "too many neighbour ranks");
+  NRSB_REQUIRE((int)peers.size() <= 64, "too many neighbour ranks");
   oogs_dev_t* d = g_dev[this].get();
   ++epoch;
   HaloExchangeDev H = make_dev(this, d, (int)(epoch & 1ull));
@@ -460,6 +468,15 @@ int oogs_t::begin_fused(FusedHalo* F, dlong NhaloElements, dlong stride)
   ++epoch;
   fusedTarget += (unsigned long long)NhaloElements;
   F->H = make_dev(this, d, (int)(epoch & 1ull));
+  // one batch of 16 send entries per pusher thread (224 threads per CTA), between 2 and kFlagSlots pushers;
+  // every pusher is an SM the element work does not get
+  {
+    static const int forced = getenv("NRSB_NPUSH") ? atoi(getenv("NRSB_NPUSH")) : 0;
+    int np = (int)((F->H.nSend + 224 * 16 - 1) / (224 * 16));
+    np = np < 2 ? 2 : (np > kFlagSlots ? kFlagSlots : np);
+    if (forced >= 1 && forced <= kFlagSlots) np = forced;
+    F->nPush = np;
+  }
   F->NhaloElements = NhaloElements;
   F->counter = fusedCounter.p;
   F->target = fusedTarget;
