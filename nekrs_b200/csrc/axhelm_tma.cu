@@ -579,6 +579,9 @@ int ax_tma_launch(int Nq, int variant, dlong Nelements, const dlong* elementList
                                                   nullptr, nullptr, dot);
   // NSTAGES must be a multiple of NGROUPS: group g then only ever touches stages == g (mod NGROUPS),
   // i.e. it owns a private sub-ring, and every mbarrier wait is at most one phase behind.
+  // Helmholtz stages carry a seventh plane (GwJ): 6 x 32 KB + work buffers exceed the 227 KB of an SM for the
+  // 3x6 / 5x5 (fp64) and 6x12 / 8x8 (fp32) rings, so the Helmholtz operator always takes the 4-stage ring.
+  if (!poisson) variant = 4;
   if (sizeof(T) == 8) {
     if (variant == 4) { NRSB_TMA(4, 4) }
     if (variant == 5) {

@@ -20,6 +20,7 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line)
   char buf[512];
   snprintf(buf, sizeof(buf), "CUDA error %d (%s) in %s at %s:%d", (int)e, cudaGetErrorString(e), what, file, line);
   g_last_error = buf;
+  cudaGetLastError();  // the runtime also latches the error: clear it, or the next launch check reports it again
   return NRSB_ERR_CUDA;
 }
 

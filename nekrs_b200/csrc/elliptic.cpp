@@ -197,7 +197,7 @@ int ellipticOperator(elliptic_t* elliptic, const T* o_q, T* o_Aq, bool masked, A
   using P = prec_traits<T>;
   const int axv = elliptic->ax_variant[P::idx] < 0 ? ax_default_variant(mesh->Nq, (int)sizeof(T))
                                                    : elliptic->ax_variant[P::idx];
-  const bool gsInLaunch = elliptic->fusedGsAx && mesh->Nq == 8 && elliptic->Nfields == 1 && axv >= 4;
+  const bool gsInLaunch = elliptic->fusedGsAx && elliptic->poisson && mesh->Nq == 8 && elliptic->Nfields == 1 && axv >= 4;
   FusedRows FR;
   if (gsInLaunch) {
     if (!elliptic->fusedArrive.p) {
@@ -218,7 +218,8 @@ int ellipticOperator(elliptic_t* elliptic, const T* o_q, T* o_Aq, bool masked, A
     elliptic->fusedArriveTarget = FR.target;
     return rc;
   }
-  if (elliptic->overlap && elliptic->fusedHaloAx && mesh->Nq == 8 && elliptic->Nfields == 1 &&
+  // (the fused launches use the 6-stage ring, which has no room for the Helmholtz GwJ plane: Poisson only)
+  if (elliptic->overlap && elliptic->fusedHaloAx && elliptic->poisson && mesh->Nq == 8 && elliptic->Nfields == 1 &&
       elliptic->ax_variant[P::idx] != 0 && mesh->NglobalGatherElements > 0 && oogs->peers.size() <= 32) {
     // ONE launch: Ax over [halo elements, interior elements]; a service warp per CTA pushes the halo partial
     // sums over NVLink as soon as the halo elements are stored.  The mask moves to finish (masked nodes

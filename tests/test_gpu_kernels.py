@@ -54,7 +54,7 @@ def test_axhelm_poisson(orc, N, dt, variant):
     assert np.all(out.reshape(E, Np)[untouched] == -3.0)
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 4, 5, 6, -1])  # 4-6, -1: TMA ring (constant coefficients), else pencil
 @pytest.mark.parametrize("lambda_field", [False, True])
 def test_axhelm_helmholtz(orc, variant, lambda_field):
     N, E = 7, 11
