@@ -31,6 +31,8 @@ sys.path.insert(0, ROOT)
 
 N_ORDER = 7
 NEL_PER_RANK = (16, 16, 16)  # 4096 elements per GPU
+WORKLOAD = ("nekrs-bench axhelm+ogs fused operator, box mesh E=4096 per GPU, N=7, fp64, all-Dirichlet mask "
+            "(BASELINE.json configs[1])")
 
 
 def algorithmic_bytes(N, w):
@@ -170,7 +172,8 @@ def run_reference(args):
         "impl": "reference", "metric": "GDOF/s fused Ax+gather-scatter (N=7 fp64)", "value": val, "unit": "GDOF/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "nekrs-bench axhelm+ogs fused operator, box mesh E=4096, N=7, fp64 (CPU arm)"},
+        "config": {"workload": WORKLOAD, "elements_per_gpu": E, "N": N_ORDER,
+                   "arm": "reference SERIAL kernels on the host cores (no GPU work)"},
         "cpu_baseline": {"value": val, "unit": "GDOF/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": "GDOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -273,8 +276,7 @@ def run_ours(args):
         "metric": "GDOF/s fused Ax+gather-scatter (N=7 fp64)", "value": value, "unit": "GDOF/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "nekrs-bench axhelm+ogs fused operator, box mesh E=4096 per GPU, N=7, fp64, "
-                               "all-Dirichlet mask", "elements_per_gpu": E, "N": N,
+        "config": {"workload": WORKLOAD, "elements_per_gpu": E, "N": N,
                    "l2": "inputs larger than L2: the K steps rotate over 3 independent input sets of 151 MB each "
                          "(ggeo+q+Aq; 453 MB > 126 MB L2), launched back to back between one CUDA-event pair",
                    "ax_variant": bench.ax_variant, "partition": "brick %s" % (bench.proc_grid,)},
