@@ -237,7 +237,7 @@ class OperatorBench:
         self.ax_variant = self.elliptic.autotune()[0]
         for ell, _, _ in self.sets[1:]:
             ell.set_ax_variant(8, self.ax_variant)
-        self.launches_per_step = 2 if nranks == 1 else 4
+        self.launches_per_step = 2  # axhelm (+ in-launch halo push on several ranks), gather-scatter / finish
         self._ev = [lib.Event() for _ in range(3)]
         self._k = 0
 
