@@ -38,8 +38,10 @@ bool pdl_enabled(bool producer)
 
 int ax_default_variant(int Nq, int precision)
 {
-  (void)precision;
   if (Nq == 8) return 5;  // persistent TMA-ring kernel (axhelm_tma.cu)
+  // measured (profiles/r1_sweep_ax_N3to9_v2.json, E=4096): in fp64 the >= 512-threads-per-SM build of the pencil
+  // kernel (variant 2) spills at Nq = 7 and Nq >= 9 (N=9: 156 us against 88 us for variant 1)
+  if (precision == 8 && (Nq == 7 || Nq >= 9)) return 1;
   return Nq >= 3 ? 2 : 0;
 }
 
