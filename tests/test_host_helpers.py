@@ -81,3 +81,65 @@ def test_topology_discovery_two_ranks_gloo(tmp_path):
     outs = [p.communicate(timeout=240)[0] for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
+
+
+WORKER_GS = r'''
+import os, sys
+import numpy as np
+import torch.distributed as dist
+sys.path.insert(0, %(root)r)
+from nekrs_b200 import meshgen, parallel
+from oracle import kernels, sem
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%(port)d", rank=int(sys.argv[1]), world_size=2)
+rank = dist.get_rank()
+comm = parallel.Comm(dist, create_handle=False)
+orc = kernels.Orc()
+N, nel = 3, (4, 3, 2)
+whole = meshgen.box_mesh(N, nel, kershaw_eps=0.3)
+part = meshgen.box_mesh(N, nel, kershaw_eps=0.3, rank=rank, nranks=2)
+topo = parallel.discover_topology(part.global_ids, comm)
+# local elements -> global element index (brick partition, lexicographic inside the brick)
+x0, y0, z0 = part.brick_lo
+ex, ey, ez = part.brick_n
+iz, iy, ix = np.meshgrid(np.arange(z0, z0 + ez), np.arange(y0, y0 + ey), np.arange(x0, x0 + ex), indexing="ij")
+gelem = (ix + nel[0] * (iy + nel[1] * iz)).ravel()
+Np = part.Np
+sel = (gelem[:, None] * Np + np.arange(Np)[None, :]).ravel()
+assert np.array_equal(whole.global_ids[sel], part.global_ids)     # same numbering on the brick
+# reference: gather-scatter of a seeded E-vector on the WHOLE mesh, one rank
+v_whole = np.random.Generator(np.random.PCG64(5)).random(whole.global_ids.size)
+ref = v_whole.copy()
+orc.gs_add(sem.Ogs(whole.global_ids), ref)
+# distributed: rows that never leave the rank are summed locally; for shared ids every rank forms its partial
+# sum, the partials travel (here: allgather), and are added in ascending rank order (oogs semantics)
+v = v_whole[sel].copy()
+ids = part.global_ids
+shared = np.isin(ids, topo.shared_ids)
+loc_ids = ids.copy(); loc_ids[shared] = 0
+orc.gs_add(sem.Ogs(loc_ids), v)
+part_sum = np.zeros(topo.shared_ids.size)
+pos = np.searchsorted(topo.shared_ids, ids[shared])
+np.add.at(part_sum, pos, v_whole[sel][shared])
+both = comm.allgather_array(part_sum)
+ids_all = comm.allgather_array(topo.shared_ids)
+assert np.array_equal(ids_all[0], ids_all[1])                     # 2 ranks: both share exactly the same ids
+total = both[0] + both[1]
+v[shared] = total[pos]
+err = np.max(np.abs(v - ref[sel])) / np.max(np.abs(ref))
+assert err < 1e-14, err
+dist.barrier()
+dist.destroy_process_group()
+print("ok", rank)
+'''
+
+
+def test_distributed_gather_scatter_two_ranks_gloo(tmp_path):
+    """N > 1 host path on CPU: brick partition + topology discovery + partial sums exchanged between two gloo ranks
+    reproduce the single-rank oracle gather-scatter on the whole mesh."""
+    script = tmp_path / "wgs.py"
+    script.write_text(WORKER_GS % {"root": ROOT, "port": 29100 + os.getpid() % 300})
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                              text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
