@@ -221,9 +221,10 @@ int ellipticOperator(elliptic_t* elliptic, const T* o_q, T* o_Aq, bool masked, A
   // (the fused launches use the 6-stage ring, which has no room for the Helmholtz GwJ plane: Poisson only)
   if (elliptic->overlap && elliptic->fusedHaloAx && elliptic->poisson && mesh->Nq == 8 && elliptic->Nfields == 1 &&
       elliptic->ax_variant[P::idx] != 0 && mesh->NglobalGatherElements > 0 && oogs->peers.size() <= 32) {
-    // ONE launch: Ax over [halo elements, interior elements]; a service warp per CTA pushes the halo partial
-    // sums over NVLink as soon as the halo elements are stored.  The mask moves to finish (masked nodes
-    // belong to no row of the masked handle, so it commutes with every sum).
+    // ONE launch: Ax over [halo elements, interior elements]; the last F.nPush CTAs of the grid do no element work,
+    // they push the halo partial sums over NVLink as soon as the halo elements are stored (oogs::begin_fused sizes
+    // nPush from the send table).  The mask moves to finish (masked nodes belong to no row of the masked handle,
+    // so it commutes with every sum).
     FusedHalo F;
     if ((rc = oogs->begin_fused(&F, mesh->NglobalGatherElements, elliptic->fieldOffset))) return rc;
     // developer aid (NRSB_OP_TIMING=1): per-kernel times of the pipelined operator, no host sync per step

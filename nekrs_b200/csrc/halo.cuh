@@ -156,7 +156,7 @@ __device__ __forceinline__ void halo_pack_flat(const HaloExchangeDev& H, const g
 // what the fused axhelm kernel needs besides the exchange itself
 struct FusedHalo {
   HaloExchangeDev H;
-  int nPush = kFlagSlots;              // CTAs of the launch that only push halo sums (no element work)
+  int nPush = 8;                       // CTAs of the launch that only push halo sums (set by oogs::begin_fused)
   dlong NhaloElements = 0;             // the first NhaloElements entries of the element list touch halo rows
   unsigned long long* counter = nullptr;  // monotonically increasing count of finished halo elements
   unsigned long long target = 0;          // value of *counter once this launch's halo elements are all stored
