@@ -63,8 +63,10 @@ class OMesh:
 class OElliptic:
     """elliptic_t for one mesh (solver or MG level)."""
 
-    def __init__(self, orc: Orc, mesh: OMesh, options: dict):
+    def __init__(self, orc: Orc, mesh: OMesh, options: dict, poisson=True, lambda0=1.0, lambda1=0.0):
         self.orc, self.mesh, self.options = orc, mesh, options
+        # constant coefficients: A = lambda0 * stiffness [+ lambda1 * mass]  (p_poisson, ellipticOperator.cpp:83-93)
+        self.poisson, self.lambda0, self.lambda1 = bool(poisson), float(lambda0), float(lambda1)
         self.mask_ids, _ = sem.dirichlet_mask_ids(mesh.N, mesh.E, mesh.EToB, mesh.ogs, orc)
         ids = mesh.global_ids.copy()
         ids[self.mask_ids] = 0
@@ -72,14 +74,18 @@ class OElliptic:
         self.inv_degree = self.ogs.inv_degree
         self.inv_degree_f = self.inv_degree.astype(f32)
         etob = mesh.EToB
-        self.allNeumann = int(not np.any((etob > 0) & (etob != 4)))
+        # the null space only exists for the pure Poisson operator (ellipticSetup.cpp:182-204)
+        self.allNeumann = int(self.poisson and not np.any((etob > 0) & (etob != 4)))
 
     def ax(self, q, Aq):
         m = self.mesh
-        if q.dtype == np.float64:
-            self.orc.ax(m.N, m.element_list, m.ggeo, m.D, q, Aq)
+        dt = q.dtype.type
+        g, D = (m.ggeo, m.D) if q.dtype == np.float64 else (m.ggeo_f, m.D_f)
+        if self.poisson and self.lambda0 == 1.0:
+            self.orc.ax(m.N, m.element_list, g, D, q, Aq)
         else:
-            self.orc.ax(m.N, m.element_list, m.ggeo_f, m.D_f, q, Aq)
+            self.orc.ax(m.N, m.element_list, g, D, q, Aq, np.array([self.lambda0], dtype=dt),
+                        np.array([self.lambda1], dtype=dt), poisson=self.poisson)
 
     def apply_mask(self, v):
         self.orc.mask(self.mask_ids, v)
@@ -103,6 +109,9 @@ class OElliptic:
         d += 2 * G[:, 1] * dd[None, None, None, :] * dd[None, None, :, None]
         d += 2 * G[:, 4] * dd[None, None, None, :] * dd[None, :, None, None]
         d += 2 * G[:, 3] * dd[None, None, :, None] * dd[None, :, None, None]
+        d *= self.lambda0
+        if not self.poisson:
+            d += self.lambda1 * G[:, 6]  # mass term: lambda1 * GwJ
         diag = np.ascontiguousarray(d.reshape(-1).astype(dtype))
         self.orc.gs_add(self.ogs, diag)
         return (dtype(1) / diag).astype(dtype)
@@ -573,7 +582,7 @@ class CoarseJPCG:
 class OSolver:
     """ellipticSolveSetup + ellipticSolve for the pressure solve on one rank."""
 
-    def __init__(self, hexmesh, options: dict, orc: Orc = None):
+    def __init__(self, hexmesh, options: dict, orc: Orc = None, poisson=True, lambda0=1.0, lambda1=0.0):
         from nekrs_b200 import meshgen  # mesh/input generator (numbering at the level orders)
         self.orc = orc or Orc()
         self.options = {k.upper(): str(v).upper() for k, v in options.items()}
@@ -582,7 +591,9 @@ class OSolver:
         m = OMesh(self.orc, hexmesh.N, hexmesh.Nelements, hexmesh.x, hexmesh.y, hexmesh.z, hexmesh.global_ids,
                   hexmesh.EToB)
         self.mesh = m
-        self.ell = OElliptic(self.orc, m, o)
+        self.ell = OElliptic(self.orc, m, o, poisson=poisson, lambda0=lambda0, lambda1=lambda1)
+        if not poisson or lambda0 != 1.0:
+            assert not compare(o, "PRECONDITIONER", "MULTIGRID"), "the multigrid restatement is Poisson-only"
         per = 1024 // 8
         self.fieldOffset = ((m.Nlocal + per - 1) // per) * per
         self.levels = []

@@ -130,3 +130,36 @@ def test_partition_covers_mesh():
         ids.append(p.global_ids)
     assert ne == whole.Nelements
     assert np.array_equal(np.unique(np.concatenate(ids)), np.unique(whole.global_ids))
+
+
+def test_helmholtz_branch_of_the_driver(orc):
+    """oracle/driver.py with p_poisson = 0: the diagonal (ellipticBlockBuildDiagonalHex3D.okl: lambda0 * stiffness
+    diagonal + lambda1 * GwJ) equals the operator applied to unit vectors, and Jacobi-PCG reproduces a manufactured
+    solution.  (The product's Helmholtz handle is checked on the GPU in tests/test_gpu_elliptic.py.)"""
+    from nekrs_b200 import meshgen
+    from oracle import driver
+    lam0, lam1 = 1.3, 0.7
+    # one deformed element: no shared nodes, so gather-scatter is the identity and 1/invDiag is the local diagonal
+    m1 = meshgen.box_mesh(2, (1, 1, 1), kershaw_eps=0.4)
+    s1 = driver.OSolver(m1, {"SOLVER": "PCG", "PRECONDITIONER": "JACOBI"}, orc, poisson=False, lambda0=lam0, lambda1=lam1)
+    n1 = m1.Nelements * m1.Np
+    diag = np.zeros(n1)
+    for i in range(n1):
+        e_i, col = np.zeros(n1), np.zeros(n1)
+        e_i[i] = 1.0
+        s1.ell.ax(e_i, col)
+        diag[i] = col[i]
+    assert np.max(np.abs(1.0 / s1.inv_diag - diag) / diag) < 1e-13
+    # manufactured solution on a 3x2x2 kershaw mesh
+    mesh = meshgen.box_mesh(3, (3, 2, 2), kershaw_eps=0.4)
+    opts = {"SOLVER": "PCG", "PRECONDITIONER": "JACOBI", "MAXIMUM ITERATIONS": "400", "SOLVER TOLERANCE": "1e-10",
+            "LINEAR SOLVER STOPPING CRITERION": "RELATIVE"}
+    s = driver.OSolver(mesh, opts, orc, poisson=False, lambda0=lam0, lambda1=lam1)
+    x_true = np.sin(np.pi * mesh.x.ravel()) * np.sin(np.pi * mesh.y.ravel()) * np.sin(np.pi * mesh.z.ravel())
+    x_true[s.ell.mask_ids] = 0.0
+    b = np.zeros(x_true.size)
+    s.ell.ax(x_true, b)                       # unassembled right-hand side, as ellipticSolve expects
+    x = s.solve(b, np.zeros(x_true.size))
+    assert 0 < s.Niter < 400
+    assert np.max(np.abs(x - x_true)) / np.max(np.abs(x_true)) < 1e-7
+    assert s.ell.allNeumann == 0
