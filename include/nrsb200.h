@@ -238,6 +238,10 @@ int nrsb_elliptic_solve_host(nrsb_elliptic_t h, const double* rhs_host, double* 
  * (0 = the fp64 solver itself when precision = 8; fp32 instances live on the MG levels) */
 int nrsb_elliptic_operator(nrsb_elliptic_t h, int level, int precision, const void* d_q, void* d_Aq, int masked);
 int nrsb_elliptic_operator_host(nrsb_elliptic_t h, const double* q_host, double* Aq_host);
+/* fp64 operator + q^T A q in one call: the p^T A p of PCG.cpp:150-157 (weightedInnerProdMany of p and Ap with
+ * invDegree), here taken from the axhelm launch itself when FUSED DOT AX is on (*fromAxLaunch = 1) */
+int nrsb_elliptic_operator_dot(nrsb_elliptic_t h, const double* d_q, double* d_Aq, int masked, double* qAq,
+                               int* fromAxLaunch);
 /* the same, queued: upload, operator and download of consecutive calls overlap (two staging slots, both copy
  * engines); q_host / Aq_host should be pinned and must stay valid until nrsb_elliptic_host_wait returns */
 int nrsb_elliptic_operator_host_async(nrsb_elliptic_t h, const double* q_host, double* Aq_host);
@@ -264,6 +268,12 @@ int nrsb_elliptic_set_ax_variant(nrsb_elliptic_t h, int precision, int variant);
 int nrsb_elliptic_set_stream(nrsb_elliptic_t h, void* stream);
 /* kernel-variant autotuning as in benchmarkAx (src/bench/axHelm/benchmarkAx.cpp:140-146,289-305) */
 int nrsb_elliptic_autotune(nrsb_elliptic_t h, int* variant_fp64, int* variant_fp32);
+
+/* determineMGLevels (MG/determineMGLevels.cpp:58-95): level orders for solver order N under the given options
+ * ("KEY=VALUE" lines: MULTIGRID SMOOTHER, MULTIGRID SCHEDULE); count = number of levels */
+int nrsb_mg_levels(int N, const char* options, int* levels_out, int capacity, int* count);
+/* 1 when every coarsen/prolongate pair and Schwarz size of that schedule is instantiated in this library */
+int nrsb_mg_schedule_supported(int N, const char* options);
 
 /* setup helpers exposed for parity tests */
 int nrsb_gll(int N, double* z_host, double* w_host, double* D_host);

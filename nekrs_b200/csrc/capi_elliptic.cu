@@ -280,6 +280,31 @@ int nrsb_elliptic_operator(nrsb_elliptic_t h, int level, int precision, const vo
                         : ellipticOperator<float>(e, (const float*)d_q, (float*)d_Aq, masked != 0);
 }
 
+/* fp64 operator that also returns q^T A q (what PCG's p^T A p is taken from, PCG.cpp:150-157).  With FUSED DOT AX
+ * (default) the value is the fold of the per-CTA energy-form partials the persistent axhelm launch leaves behind;
+ * otherwise (or when the launch path cannot provide them) the reference's weighted inner product
+ * sum invDegree * q * Aq after the gather-scatter.  *fromAxLaunch tells which one was taken. */
+int nrsb_elliptic_operator_dot(nrsb_elliptic_t h, const double* d_q, double* d_Aq, int masked, double* qAq,
+                               int* fromAxLaunch)
+{
+  NRSB_REQUIRE(h && d_q && d_Aq && qAq, "NULL argument");
+  elliptic_t* e = &h->impl;
+  int rc;
+  if (!e->o_dotPartials.p)
+    if ((rc = e->o_dotPartials.alloc(kNumSMs))) return rc;
+  AxDot dot;
+  dot.partials = e->o_dotPartials.p;
+  if ((rc = ellipticOperator<double>(e, d_q, d_Aq, masked != 0, e->fusedDotAx ? &dot : nullptr))) return rc;
+  double* S = e->o_scal.p;
+  if (dot.n > 0)
+    rc = sum_launch<double>(dot.n, dot.partials, S + 7, e->ws, e->stream);  // slot 7 = S_SUM
+  else
+    rc = wdot_launch<double>(e->mesh->Nlocal, e->o_invDegree, d_q, d_Aq, S + 7, e->ws, e->stream);
+  if (rc) return rc;
+  if (fromAxLaunch) *fromAxLaunch = dot.n > 0 ? 1 : 0;
+  return e->read_scalars(7, 1, qAq);
+}
+
 int nrsb_elliptic_operator_host(nrsb_elliptic_t h, const double* q_host, double* Aq_host)
 {
   NRSB_REQUIRE(h && q_host && Aq_host, "NULL argument");
@@ -532,6 +557,7 @@ int nrsb_elliptic_set_option(nrsb_elliptic_t h, const char* key, const char* val
   h->impl.options.setArgs(k, v);
   // kershaw.udf:47-53 switches PRECONDITIONER/SOLVER between benchmarks and re-runs the preconditioner setup
   if (k == "PRECONDITIONER") return ellipticPreconditionerSetup(&h->impl);
+  if (k == "SOLVER" || k == "PGMRES RESTART") return ellipticKrylovWorkspace(&h->impl);
   return NRSB_OK;
 }
 
@@ -601,6 +627,30 @@ int nrsb_elliptic_autotune(nrsb_elliptic_t h, int* variant_fp64, int* variant_fp
 }
 
 // ------------------------------------------------------------------------------------------ helpers
+int nrsb_mg_levels(int N, const char* options, int* levels_out, int capacity, int* count)
+{
+  NRSB_REQUIRE(N >= 1 && N <= 11 && count, "N out of range (1..11) or count is NULL");
+  options_t o;
+  parse_options(options ? options : "", o);
+  const std::vector<int> lv = determineMGLevels(o, N);
+  *count = (int)lv.size();
+  if (levels_out)
+    for (int i = 0; i < (int)lv.size() && i < capacity; ++i) levels_out[i] = lv[i];
+  return NRSB_OK;
+}
+int nrsb_mg_schedule_supported(int N, const char* options)
+{
+  options_t o;
+  parse_options(options ? options : "", o);
+  if (N < 1 || N > 11) return 0;
+  const std::vector<int> lv = determineMGLevels(o, N);
+  const bool schwarzSm = o.compareArgs("MULTIGRID SMOOTHER", "ASM") || o.compareArgs("MULTIGRID SMOOTHER", "RAS");
+  for (size_t n = 0; n < lv.size(); ++n) {
+    if (n > 0 && !transfer_supported(lv[n - 1] + 1, lv[n] + 1)) return 0;
+    if (schwarzSm && lv[n] > 1 && !fdm_supported(lv[n] + 1)) return 0;
+  }
+  return 1;
+}
 int nrsb_gll(int N, double* z_host, double* w_host, double* D_host)
 {
   NRSB_REQUIRE(N >= 1 && N <= 15, "N out of range");

@@ -289,6 +289,32 @@ int ellipticOperator(elliptic_t* elliptic, const T* o_q, T* o_Aq, bool masked, A
     return oogs->finish<T>(o_Aq, elliptic->Nfields, elliptic->fieldOffset, gs_op::add,
                            masked ? elliptic->NmaskedLocal : 0, elliptic->o_maskIdsLocal.p, elliptic->stream);
   }
+  // single rank, persistent TMA-ring axhelm: the mask + gather-scatter run beside the axhelm launch (gs_stream.cu),
+  // chunk by chunk of finished elements, instead of as a second pass after it
+  if (elliptic->streamedGs && oogs->ogs->NhaloGather == 0 && mesh->Nq == 8 && elliptic->Nfields == 1 && axv >= 4 &&
+      mesh->Nelements >= 2 * kNumSMs) {
+    if (!elliptic->gsStream) {
+      elliptic->gsStream.reset(new gs_stream_t());
+      std::vector<dlong> pos(mesh->Nelements);
+      for (dlong e = 0; e < mesh->Nelements; ++e) pos[e] = e;  // o_elementList is the identity
+      if ((rc = elliptic->gsStream->build(oogs->ogs, elliptic->maskIds, pos, mesh->Np,
+                                          std::min<dlong>(kNumSMs, mesh->Nelements))))
+        return rc;
+    }
+    gs_stream_t* G = elliptic->gsStream.get();
+    AxDot extras;
+    AxDot* d = dot ? dot : &extras;
+    d->chunkDone = G->d_done;
+    d->chunkLen = G->chunkLen;
+    d->chunksCounted = false;
+    if ((rc = ellipticAxDot<T>(elliptic, mesh->Nelements, mesh->o_elementList.p, o_q, o_Aq, d))) return rc;
+    if (d->chunksCounted) {
+      ++G->epoch;
+      return gs_stream_launch<T>(G->dev(nm > 0), o_Aq, elliptic->stream);
+    }
+    return oogs->startFinish<T>(o_Aq, elliptic->Nfields, elliptic->fieldOffset, gs_op::add, nm, elliptic->o_maskIds.p,
+                                elliptic->stream);
+  }
   if ((rc = ellipticAxDot<T>(elliptic, mesh->Nelements, mesh->o_elementList.p, o_q, o_Aq, dot))) return rc;
   if (oogs->ogs->NhaloGather) {
     // halo rows are packed from masked values: mask first
@@ -383,6 +409,40 @@ int elliptic_workspace(elliptic_t* elliptic)
   return NRSB_OK;
 }
 
+// Krylov workspace that depends on SOLVER / PGMRES RESTART (ellipticSetup.cpp:225-262, GmresData in
+// PGMRES.cpp:31-68).  Called from ellipticSolveSetup and again whenever nrsb_elliptic_set_option changes one of
+// those keys (kershaw.udf:47-53 switches SOLVER between its benchmarks), so that pgmres() never runs on buffers
+// sized for another configuration.
+int ellipticKrylovWorkspace(elliptic_t* elliptic)
+{
+  options_t& options = elliptic->options;
+  if (!options.compareArgs("SOLVER", "PGMRES")) return NRSB_OK;
+  int rc;
+  const size_t fo = (size_t)elliptic->fieldOffset * elliptic->Nfields;
+  elliptic->nRestartVectors = 15;
+  options.getArgs("PGMRES RESTART", elliptic->nRestartVectors);
+  NRSB_REQUIRE(elliptic->nRestartVectors >= 1 && elliptic->nRestartVectors <= kMaxRed,
+               "PGMRES RESTART must be in 1..16");
+  const int m = elliptic->nRestartVectors;
+  const bool flexible = options.compareArgs("SOLVER", "FLEXIBLE");
+  NRSB_CUDA(cudaStreamSynchronize(elliptic->stream));  // buffers may be re-allocated: nothing may still use them
+  if (elliptic->o_V.n < fo * m)
+    if ((rc = elliptic->o_V.alloc(fo * m))) return rc;
+  if (elliptic->o_Z.n < fo * (flexible ? m : 1))
+    if ((rc = elliptic->o_Z.alloc(fo * (flexible ? m : 1)))) return rc;
+  if (elliptic->o_y.n < (size_t)kMaxRed)
+    if ((rc = elliptic->o_y.alloc(kMaxRed))) return rc;
+  if (!flexible && elliptic->o_rtmp.n < fo)
+    if ((rc = elliptic->o_rtmp.alloc(fo))) return rc;
+  elliptic->gmres_H.assign((size_t)(m + 1) * (m + 1), 0.0);
+  elliptic->gmres_sn.assign(m, 0.0);
+  elliptic->gmres_cs.assign(m, 0.0);
+  elliptic->gmres_s.assign(m + 1, 0.0);
+  elliptic->gmres_y.assign(m, 0.0);
+  NRSB_CUDA(cudaDeviceSynchronize());  // dbuf::alloc zero-fills on the legacy stream
+  return NRSB_OK;
+}
+
 int ellipticSolveSetup(elliptic_t* elliptic)
 {
   mesh_t* mesh = elliptic->mesh;
@@ -436,27 +496,11 @@ int ellipticSolveSetup(elliptic_t* elliptic)
   // 42.0 vs 39.4 us per operator at E=4096: off unless asked for
   elliptic->fusedGsAx = options.compareArgs("FUSED GS AX", "TRUE") || getenv("NRSB_FUSED_GS") != nullptr;
   elliptic->fusedDotAx = !options.compareArgs("FUSED DOT AX", "FALSE") && getenv("NRSB_NO_FUSED_DOT") == nullptr;
+  elliptic->streamedGs = !options.compareArgs("STREAMED GS", "FALSE") && getenv("NRSB_NO_STREAMED_GS") == nullptr;
   elliptic->overlap = elliptic->ogs->NhaloGather > 0 && !options.compareArgs("ENABLE GS COMM OVERLAP", "FALSE") &&
                       mesh->NlocalGatherElements > 0;
 
-  if (options.compareArgs("SOLVER", "PGMRES")) {
-    elliptic->nRestartVectors = 15;
-    options.getArgs("PGMRES RESTART", elliptic->nRestartVectors);
-    NRSB_REQUIRE(elliptic->nRestartVectors >= 1 && elliptic->nRestartVectors <= kMaxRed,
-                 "PGMRES RESTART must be in 1..16");
-    const int m = elliptic->nRestartVectors;
-    const bool flexible = options.compareArgs("SOLVER", "FLEXIBLE");
-    if ((rc = elliptic->o_V.alloc(fo * m))) return rc;
-    if ((rc = elliptic->o_Z.alloc(fo * (flexible ? m : 1)))) return rc;
-    if ((rc = elliptic->o_y.alloc(m))) return rc;
-    if (!flexible)
-      if ((rc = elliptic->o_rtmp.alloc(fo))) return rc;
-    elliptic->gmres_H.assign((size_t)(m + 1) * (m + 1), 0.0);
-    elliptic->gmres_sn.assign(m, 0.0);
-    elliptic->gmres_cs.assign(m, 0.0);
-    elliptic->gmres_s.assign(m + 1, 0.0);
-    elliptic->gmres_y.assign(m, 0.0);
-  }
+  if ((rc = ellipticKrylovWorkspace(elliptic))) return rc;
 
   if ((rc = ellipticPreconditionerSetup(elliptic))) return rc;
 
@@ -671,6 +715,10 @@ int pgmres(elliptic_t* elliptic, double* o_r, double* o_x, double tol, int MAXIT
   const bool flexible = elliptic->options.compareArgs("SOLVER", "FLEXIBLE");
   const long fo = (long)elliptic->fieldOffset * elliptic->Nfields;
   const long N = mesh->Nlocal;
+  NRSB_REQUIRE(m >= 1 && elliptic->o_V.n >= (size_t)fo * m && elliptic->o_Z.n >= (size_t)fo * (flexible ? m : 1) &&
+                   elliptic->o_y.p && (flexible || elliptic->o_rtmp.n >= (size_t)fo) &&
+                   elliptic->gmres_H.size() == (size_t)(m + 1) * (m + 1),
+               "pgmres: workspace was not set up for this SOLVER / PGMRES RESTART (ellipticKrylovWorkspace)");
   double* o_w = elliptic->o_p.p;
   double* o_Ax = elliptic->o_Ap.p;
   double* o_V = elliptic->o_V.p;

@@ -254,14 +254,17 @@ static int fused_launch(int restrict_, dlong Nelements, const dlong* elementList
     case 10: CALL(10)                                               \
     case 11: CALL(11)                                               \
     case 12: CALL(12)                                               \
+    case 13: CALL(13)                                               \
+    case 14: CALL(14)                                               \
     default:                                                        \
-      set_last_error("FDM: unsupported Nq (supported: 2..10)");     \
+      set_last_error("FDM: unsupported Nq (supported: 2..12)");     \
       return NRSB_ERR_INVALID;                                      \
   }
 
 int fused_fdm_v1_launch(int Nq, int restrict_, dlong Nelements, const dlong* elementList, float* Su, const float* Sx,
                         const float* Sy, const float* Sz, const float* invL, const float* wts, float* u,
                         cudaStream_t stream, int epb);
+bool fdm_supported(int Nq) { return Nq + 2 >= 4 && Nq + 2 <= 14; }
 static int g_fdm_variant = 1;  // 0: one pencil per thread (this file); 1: register-blocked pairs (fdm_v1.cu)
 void set_fdm_variant(int v) { g_fdm_variant = v; }
 

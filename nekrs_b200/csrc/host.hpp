@@ -319,6 +319,9 @@ class elliptic_t {
   bool fusedDotAx = true;
   dbuf<double> o_dotPartials;
   unsigned long long fusedArriveTarget = 0;
+  // mask + on-rank gather-scatter by a co-resident kernel WHILE the persistent axhelm launch runs (gs_stream.cu)
+  bool streamedGs = true;
+  std::unique_ptr<gs_stream_t> gsStream;
   dlong Nmasked = 0, NmaskedLocal = 0, NmaskedGlobal = 0;
   dbuf<dlong> o_maskIds, o_maskIdsLocal, o_maskIdsGlobal;
   std::vector<dlong> maskIds;
@@ -364,6 +367,7 @@ class elliptic_t {
 
 // elliptic.cpp
 int ellipticSolveSetup(elliptic_t* elliptic);
+int ellipticKrylovWorkspace(elliptic_t* elliptic);  // (re)sizes the PGMRES buffers for the current SOLVER options
 int ellipticSolve(elliptic_t* elliptic, double* o_r, double* o_x);
 template <typename T>
 int ellipticAx(elliptic_t* elliptic, dlong NelementsList, const dlong* o_elementList, const T* o_q, T* o_Aq);

@@ -10,6 +10,13 @@ namespace nrsb {
 struct AxDot {
   double* partials = nullptr;
   int n = 0;
+  // streamed gather-scatter (gs_stream.cu): when set, the persistent axhelm launch counts every finished element of
+  // list positions [c * chunkLen, (c+1) * chunkLen) into chunkDone[c] (fence + device-scope add after the element's
+  // stores), so that a co-resident kernel can gather-scatter the rows of finished chunks while the launch runs on.
+  // Honoured by the TMA-ring variants only; `chunksCounted` tells the caller whether it was.
+  unsigned long long* chunkDone = nullptr;
+  int chunkLen = 0;
+  bool chunksCounted = false;
 };
 template <typename T>
 int ax_launch(int Nq, int variant, dlong Nelements, dlong loffset, const dlong* elementList, const T* ggeo,
@@ -40,6 +47,8 @@ int post_fdm_launch(int Nq, dlong Nelements, const float* work1, const float* wo
 // transfer.cu
 int transfer_dispatch(bool coarsen, int NqF, int NqC, dlong Nelements, const float* R_host, const float* in,
                       float* out, cudaStream_t stream);
+bool transfer_supported(int NqF, int NqC);
+bool fdm_supported(int Nq);  // extended size Nq + 2 instantiated
 int geometric_factors_launch(int Nq, dlong Nelements, const double* d_D, const double* d_gllw, const double* x,
                              const double* y, const double* z, double* ggeo, double* Jac, cudaStream_t stream);
 

@@ -42,7 +42,13 @@ int dbuf<T>::alloc(size_t count, bool zero)
     return NRSB_ERR_NOMEM;
   }
   NRSB_CUDA(e);
-  if (zero) NRSB_CUDA(cudaMemset(p, 0, count * sizeof(T)));
+  if (zero) {
+    // cudaMemset on device memory is asynchronous and runs on the legacy default stream, which is NOT ordered
+    // against cudaStreamNonBlocking streams (what nrsb_stream_create hands out): wait for it here, so that work
+    // queued on any stream right after a (lazy) allocation cannot be overtaken by the zero-fill.
+    NRSB_CUDA(cudaMemsetAsync(p, 0, count * sizeof(T), cudaStreamLegacy));
+    NRSB_CUDA(cudaStreamSynchronize(cudaStreamLegacy));
+  }
   return NRSB_OK;
 }
 template <typename T>

@@ -26,7 +26,9 @@ int elliptic_workspace(elliptic_t* elliptic);
 std::vector<int> determineMGLevels(const options_t& options, int N)
 {
   // user schedule "p=7+degree=3, p=3+degree=3, p=1, ..." (parseMultigridSchedule): only the orders matter here
-  const std::string schedule = options.getArgs("MULTIGRID SCHEDULE");
+  // (option values are upper-cased on the way in, capi_elliptic.cu parse_options)
+  std::string schedule = options.getArgs("MULTIGRID SCHEDULE");
+  for (auto& c : schedule) c = (char)tolower(c);
   if (!schedule.empty()) {
     std::vector<int> levels;
     size_t pos = 0;
@@ -53,8 +55,10 @@ std::vector<int> determineMGLevels(const options_t& options, int N)
 
 // degree of a (order, leg) pair in a user schedule; -1 if absent.  Schedule entries are listed fine
 // to coarse (down leg) and back (up leg); "p=1" alone has no smoothing degree.
-static int schedule_degree(const std::string& schedule, int order, bool downLeg)
+static int schedule_degree(const std::string& schedule_, int order, bool downLeg)
 {
+  std::string schedule = schedule_;
+  for (auto& c : schedule) c = (char)tolower(c);
   std::vector<std::pair<int, int>> entries;
   size_t pos = 0;
   while ((pos = schedule.find("p=", pos)) != std::string::npos) {
@@ -935,6 +939,23 @@ int ellipticMultiGridSetup(elliptic_t* elliptic_, precon_t* precon)
   NRSB_REQUIRE(!levelDegree.empty() && levelDegree[0] == mesh->N, "multigrid schedule must start at the solver order");
   const int numMGLevels = (int)levelDegree.size();
   const int Nmax = levelDegree[0], Nmin = levelDegree[numMGLevels - 1];
+  // every transfer pair and Schwarz size of this schedule must be instantiated: fail HERE with a clear message,
+  // not in the first V-cycle
+  {
+    const bool schwarzSm =
+        options.compareArgs("MULTIGRID SMOOTHER", "ASM") || options.compareArgs("MULTIGRID SMOOTHER", "RAS");
+    for (int n = 0; n < numMGLevels; ++n) {
+      if (n > 0 && !transfer_supported(levelDegree[n - 1] + 1, levelDegree[n] + 1)) {
+        set_last_error("multigrid schedule needs the coarsen/prolongate pair N=" + std::to_string(levelDegree[n - 1]) +
+                       " -> N=" + std::to_string(levelDegree[n]) + ", which is not instantiated (transfer.cu)");
+        return NRSB_ERR_INVALID;
+      }
+      if (schwarzSm && levelDegree[n] > 1 && !fdm_supported(levelDegree[n] + 1)) {
+        set_last_error("Schwarz smoother at N=" + std::to_string(levelDegree[n]) + " is not instantiated (fdm.cu)");
+        return NRSB_ERR_INVALID;
+      }
+    }
+  }
   precon->MGSolver.reset(new MGSolver_t());
   MGSolver_t* mg = precon->MGSolver.get();
   const bool coarseSolveOpt = options.compareArgs("MULTIGRID COARSE SOLVE", "TRUE");

@@ -150,6 +150,19 @@ static int transfer_launch(bool coarsen, dlong Nelements, const float* R_host, c
   return NRSB_OK;
 }
 
+// is the (NqFine, NqCoarse) pair instantiated?  (setup-time check + CPU test against determineMGLevels)
+bool transfer_supported(int NqF, int NqC)
+{
+  static const int pairs[][2] = {{3, 2},  {4, 2},  {4, 3},  {5, 2},  {5, 3},  {5, 4},  {6, 2},   {6, 3},  {6, 4},
+                                 {6, 5},  {7, 2},  {7, 4},  {7, 5},  {7, 6},  {8, 2},  {8, 4},   {8, 5},  {8, 6},
+                                 {8, 7},  {9, 2},  {9, 4},  {9, 6},  {9, 7},  {9, 8},  {10, 2},  {10, 4}, {10, 6},
+                                 {10, 8}, {10, 9}, {11, 2}, {11, 6}, {11, 7}, {11, 8}, {11, 9},  {11, 10}, {12, 2},
+                                 {12, 6}, {12, 7}, {12, 8}, {12, 10}, {12, 11}};
+  for (auto& p : pairs)
+    if (p[0] == NqF && p[1] == NqC) return true;
+  return false;
+}
+
 int transfer_dispatch(bool coarsen, int NqF, int NqC, dlong Nelements, const float* R_host, const float* in,
                       float* out, cudaStream_t stream)
 {
@@ -160,7 +173,8 @@ int transfer_dispatch(bool coarsen, int NqF, int NqC, dlong Nelements, const flo
   TR(3, 2) TR(4, 2) TR(4, 3) TR(5, 2) TR(5, 3) TR(5, 4) TR(6, 2) TR(6, 3) TR(6, 4) TR(6, 5)
   TR(7, 2) TR(7, 4) TR(7, 5) TR(7, 6) TR(8, 2) TR(8, 4) TR(8, 5) TR(8, 6) TR(8, 7)
   TR(9, 2) TR(9, 4) TR(9, 6) TR(9, 7) TR(9, 8) TR(10, 2) TR(10, 4) TR(10, 6) TR(10, 8) TR(10, 9)
-  TR(11, 2) TR(11, 6) TR(11, 8) TR(11, 10) TR(12, 2) TR(12, 6) TR(12, 8) TR(12, 10) TR(12, 11)
+  TR(11, 2) TR(11, 6) TR(11, 7) TR(11, 8) TR(11, 9) TR(11, 10)
+  TR(12, 2) TR(12, 6) TR(12, 7) TR(12, 8) TR(12, 10) TR(12, 11)
 #undef TR
   set_last_error("coarsen/prolongate: unsupported (NqFine, NqCoarse) pair");
   return NRSB_ERR_INVALID;

@@ -1,0 +1,167 @@
+"""GPU parity AT THE BENCHMARKED SIZES (BASELINE.json configs 2 and 3): box E = 16^3 = 4096 and kershaw
+E = 20^3 = 8000 at N = 7, against the oracle on the full mesh, through the C ABI.
+
+Why a separate file: with <= 148 elements every CTA of the persistent TMA-ring axhelm handles ONE element, so
+consumer groups 1..2, the ring wrap (i >= NSTAGES), the mbarrier phase flips, the empty[] hand-back, the
+per-CTA q^T A q partials and (streamed gather-scatter) the chunk counters never execute.  Here each CTA
+processes 27-55 elements (same check benchmarkAx.cpp:289-305 does at bench size: every variant against the
+first, 400 eps).
+
+Tolerances (BASELINE.json north_star): 1e-12 relative in fp64, 1e-5 in fp32.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from nekrs_b200 import lib, meshgen
+from nekrs_b200.elliptic import Elliptic
+from nekrs_b200.lib import DeviceBuffer as DB
+from oracle import driver
+
+pytestmark = pytest.mark.gpu
+
+OPTS = {"SOLVER": "PCG", "PRECONDITIONER": "NONE", "MAXIMUM ITERATIONS": "30", "SOLVER TOLERANCE": "1e-15"}
+CASES = {"box4096": ((16, 16, 16), 1.0), "kershaw8000": ((20, 20, 20), 0.3)}
+
+
+def relerr(a, b):
+    return np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300)
+
+
+def padded(v, n):
+    out = np.zeros(n, dtype=v.dtype)
+    out[:v.size] = v
+    return out
+
+
+@pytest.fixture(scope="module", params=list(CASES))
+def full(request, orc):
+    nel, eps = CASES[request.param]
+    mesh = meshgen.box_mesh(7, nel, kershaw_eps=eps)
+    ell = Elliptic(mesh, OPTS)
+    ref = driver.OSolver(mesh, OPTS, orc)
+    n = mesh.Nelements * mesh.Np
+    q = np.random.Generator(np.random.PCG64(11)).random(n)
+    out_ref = np.zeros(n)
+    ref.ell.operator(q, out_ref)
+    ax_ref = np.zeros(n)
+    ref.ell.ax(q, ax_ref)
+    yield dict(name=request.param, mesh=mesh, ell=ell, ref=ref, n=n, q=q, out_ref=out_ref, ax_ref=ax_ref, orc=orc)
+    ell.destroy()
+
+
+@pytest.mark.parametrize("variant", [-1, 0, 1, 4, 5, 6])
+def test_fullsize_ax_and_operator_fp64(full, variant):
+    ell, n = full["ell"], full["n"]
+    d_q = DB(like=padded(full["q"], ell.fieldOffset))
+    d_Aq = DB(like=np.full(ell.fieldOffset, -7.0))
+    ell.set_ax_variant(8, variant)
+    try:
+        ell.ax(d_q, d_Aq)
+        assert relerr(d_Aq.download()[:n], full["ax_ref"]) < 1e-12
+        for rep in range(3):  # counters / epochs of the persistent kernels are never reset
+            ell.operator(d_q, d_Aq)
+            assert relerr(d_Aq.download()[:n], full["out_ref"]) < 1e-12
+    finally:
+        ell.set_ax_variant(8, -1)
+
+
+def test_fullsize_operator_paths_bit_identical(full):
+    """The gather-scatter sums every row in the reference's order (ascending local index), whichever launch
+    structure executes it: two launches, phase 2 of the axhelm launch, or the streamed gather-scatter that runs
+    next to the axhelm launch.  Same Ax variant => same bits."""
+    mesh, ell, n = full["mesh"], full["ell"], full["n"]
+    d_q = DB(like=padded(full["q"], ell.fieldOffset))
+    outs = {}
+    for name, extra in (("two-launch", {"STREAMED GS": "FALSE"}), ("in-launch", {"FUSED GS AX": "TRUE"}),
+                        ("streamed", {"STREAMED GS": "TRUE"})):
+        e2 = Elliptic(mesh, dict(OPTS, **extra))
+        e2.set_ax_variant(8, 5)
+        d = DB.zeros(e2.fieldOffset, np.float64)
+        for rep in range(4):
+            e2.operator(d_q, d)
+        outs[name] = d.download()[:n].copy()
+        e2.operator(d_q, d, masked=False)
+        outs[name + "/unmasked"] = d.download()[:n].copy()
+        e2.destroy()
+    assert relerr(outs["two-launch"], full["out_ref"]) < 1e-12
+    for k in ("in-launch", "streamed"):
+        assert np.array_equal(outs[k], outs["two-launch"]), k
+        assert np.array_equal(outs[k + "/unmasked"], outs["two-launch/unmasked"]), k
+
+
+def test_fullsize_operator_dot(full):
+    """q^T A q out of the axhelm launch (per-CTA energy-form partials, fixed-order fold) against the oracle's
+    weighted inner product  sum invDegree * q * (Q Q^T mask A q)  (PCG.cpp:150-157) for a continuous, masked q."""
+    ell, ref, n, orc = full["ell"], full["ref"], full["n"], full["orc"]
+    q = full["q"].copy()
+    # make q continuous and masked, as PCG's p is
+    orc.gs_add(ref.ell.ogs, q)
+    q *= ref.ell.inv_degree
+    ref.ell.apply_mask(q)
+    Aq = np.zeros(n)
+    ref.ell.operator(q, Aq)
+    want = orc.weighted_inner_prod(n, ref.ell.inv_degree, q, Aq)
+    d_q, d_Aq = DB(like=padded(q, ell.fieldOffset)), DB.zeros(ell.fieldOffset, np.float64)
+    got, frm = C.c_double(0), C.c_int(-1)
+    lib.call("nrsb_elliptic_operator_dot", ell._h, lib.vp(d_q), lib.vp(d_Aq), C.c_int(1), C.byref(got), C.byref(frm))
+    assert frm.value == 1, "default path must take q^T A q from the axhelm launch"
+    assert abs(got.value - want) / abs(want) < 1e-12
+    assert relerr(d_Aq.download()[:n], Aq) < 1e-12
+    ell.set_option("FUSED DOT AX", "FALSE")
+
+
+def test_fullsize_operator_fp32(full):
+    mesh, ell, ref, n = full["mesh"], full["ell"], full["ref"], full["n"]
+    q = full["q"].astype(np.float32)
+    out_ref = np.zeros(n, dtype=np.float32)
+    ref.ell.operator(q, out_ref)
+    d_q, d_Aq = DB(like=padded(q, ell.fieldOffset)), DB.zeros(ell.fieldOffset, np.float32)
+    for variant in (-1, 1, 4, 5, 6):
+        ell.set_ax_variant(4, variant)
+        ell.operator(d_q, d_Aq, precision=4)
+        assert relerr(d_Aq.download(np.float32)[:n], out_ref) < 1e-5, variant
+    ell.set_ax_variant(4, -1)
+
+
+def test_fullsize_bp5_history(full):
+    """30 PCG iterations without preconditioner (kershaw.udf:47-53: fixed work) at the benchmarked size."""
+    if full["name"] != "kershaw8000":
+        pytest.skip("BP5 is defined on the kershaw mesh")
+    mesh, ell, ref, n = full["mesh"], full["ell"], full["ref"], full["n"]
+    rhs = meshgen.kershaw_rhs(mesh)
+    ref.solve(rhs, np.zeros(n))
+    x = np.zeros(n)
+    it = ell.solve_host(rhs, x)
+    h, hr = ell.res_history(), np.array(ref.res_history)
+    assert it == ref.Niter == 30
+    assert np.max(np.abs(h[:5] - hr[:5]) / hr[:5]) < 1e-10
+    assert np.max(np.abs(h - hr) / hr) < 1e-8
+
+
+def test_fullsize_fdm(orc):
+    """preFDM / fusedFDM / postFDM at E = 4096, N = 7 (extended Nq_e = 10) against the oracle kernels."""
+    from nekrs_b200 import ops
+    E, N = 4096, 7
+    Nq, Nqe = N + 1, N + 3
+    r = np.random.Generator(np.random.PCG64(5))
+    f32 = np.float32
+    Sx, Sy, Sz = (r.random((E, Nqe * Nqe)).astype(f32) - 0.5 for _ in range(3))
+    invL = r.random((E, Nqe ** 3)).astype(f32)
+    wts = r.random((E, Nq ** 3)).astype(f32)
+    u = r.random((E, Nqe ** 3)).astype(f32)
+    for restrict in (1, 0):
+        nout = Nq ** 3 if restrict else Nqe ** 3
+        ref = np.zeros((E, nout), dtype=f32)
+        orc.fused_fdm(E, N, ref, Sx, Sy, Sz, invL, wts, u.copy(), restrict)
+        d_Su = DB.zeros(E * nout, f32)
+        ops.fusedFDM(N, restrict, E, DB(like=np.arange(E, dtype=np.int32)), d_Su, DB(like=Sx), DB(like=Sy),
+                     DB(like=Sz), DB(like=invL), DB(like=wts), DB(like=u))
+        assert relerr(d_Su.download(f32), ref.ravel()) < 1e-5, restrict
+    v = r.random((E, Nq ** 3)).astype(f32)
+    w1_ref = np.zeros((E, Nqe ** 3), dtype=f32)
+    orc.pre_fdm(E, N, v, w1_ref)
+    d_w1 = DB.zeros(E * Nqe ** 3, f32)
+    ops.preFDM(N, E, DB(like=v), d_w1)
+    assert np.array_equal(d_w1.download(f32), w1_ref.ravel())

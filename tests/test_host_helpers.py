@@ -143,3 +143,27 @@ def test_distributed_gather_scatter_two_ranks_gloo(tmp_path):
     outs = [p.communicate(timeout=240)[0] for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
+
+
+def test_every_default_mg_schedule_is_instantiated():
+    """determineMGLevels (MG/determineMGLevels.cpp:58-95) for N = 1..11, Schwarz and non-Schwarz smoothers: every
+    coarsen/prolongate pair and every FDM size the default schedule needs exists in the library, and the C++
+    level table equals the harness' (nekrs_b200.elliptic.mg_level_orders)."""
+    import ctypes as C
+    from nekrs_b200 import lib
+    from nekrs_b200.elliptic import mg_level_orders
+    L = lib.load()
+    for sm in ("FOURTHOPTCHEBYSHEV+ASM", "FOURTHOPTCHEBYSHEV+RAS", "CHEBYSHEV+JACOBI", "DAMPEDJACOBI"):
+        opt = ("MULTIGRID SMOOTHER=%s\n" % sm).encode()
+        for N in range(1, 12):
+            out = (C.c_int * 8)()
+            cnt = C.c_int(0)
+            assert L.nrsb_mg_levels(C.c_int(N), opt, out, C.c_int(8), C.byref(cnt)) == 0
+            assert list(out[:cnt.value]) == mg_level_orders({"MULTIGRID SMOOTHER": sm}, N)
+            assert L.nrsb_mg_schedule_supported(C.c_int(N), opt) == 1, (sm, N)
+    # user schedule
+    opt = b"MULTIGRID SCHEDULE=p=7+degree=3,p=5+degree=3,p=1\nMULTIGRID SMOOTHER=FOURTHOPTCHEBYSHEV+ASM\n"
+    out = (C.c_int * 8)()
+    cnt = C.c_int(0)
+    assert L.nrsb_mg_levels(C.c_int(7), opt, out, C.c_int(8), C.byref(cnt)) == 0
+    assert list(out[:cnt.value]) == [7, 5, 1]
