@@ -473,15 +473,12 @@ __global__ void __launch_bounds__(NGROUPS* Nq* Nq + 32, 1)
       if constexpr (!kPoisson) v += r_mass[k];
       Ae[k * Nq2] = v;
     }
-    const dlong pos = blockIdx.x + (dlong)i * nAx;  // position in the element list
-    const bool haloElem = kFused && (pos < F.NhaloElements);
+    const bool haloElem = kFused && (blockIdx.x + (dlong)i * nAx < F.NhaloElements);
     group_sync(1 + g, Nq2);  // su/ss are rewritten by the next element of this group
-    if (t == 0 && (haloElem || R2.chunkDone)) {
+    if (haloElem && t == 0) {
       // the group's stores are ordered before this point by the barrier; one fence (cumulative) publishes them
       __threadfence();
-      if (haloElem) atomicAdd(F.counter, 1ull);
-      // streamed gather-scatter: this element of chunk pos / chunkLen is final in global memory
-      if (R2.chunkDone) atomicAdd(R2.chunkDone + pos / R2.chunkLen, 1ull);
+      atomicAdd(F.counter, 1ull);
     }
   }
 
@@ -555,24 +552,6 @@ static int launch_tma(dlong Nelements, const dlong* elementList, const T* ggeo, 
   if (kDot) {
     R2.dotPartials = dot->partials;
     dot->n = grid;
-  }
-  if (dot && dot->chunkDone) {
-    // only when the streamed gather-scatter kernel can sit next to this CTA on the SM (registers, shared memory);
-    // otherwise the caller takes the two-launch path
-    static int streamOk = -1;
-    if (streamOk < 0) {
-      cudaFuncAttributes fa{};
-      NRSB_CUDA(cudaFuncGetAttributes(&fa, kern));
-      streamOk = gs_stream_fits(fa.numRegs, NGROUPS * Nq * Nq + 32, smem + fa.sharedSizeBytes) ? 1 : 0;
-      if (getenv("NRSB_VERBOSE"))
-        fprintf(stderr, "[nrsb] ax_tma<%d bytes, %d groups, %d stages>: %d registers, %zu B smem: streamed gs %s\n",
-                (int)sizeof(T), NGROUPS, NSTAGES, fa.numRegs, smem, streamOk ? "co-resident" : "does not fit");
-    }
-    if (streamOk) {
-      R2.chunkDone = dot->chunkDone;
-      R2.chunkLen = dot->chunkLen > 0 ? dot->chunkLen : 1;
-      dot->chunksCounted = true;
-    }
   }
   // (Launching this kernel as a programmatic dependent launch, with the first geometric-factor slabs requested
   // before griddepcontrol.wait, was measured slower: 28-29 us per launch with the attribute, 31-33 us without it,

@@ -289,32 +289,6 @@ int ellipticOperator(elliptic_t* elliptic, const T* o_q, T* o_Aq, bool masked, A
     return oogs->finish<T>(o_Aq, elliptic->Nfields, elliptic->fieldOffset, gs_op::add,
                            masked ? elliptic->NmaskedLocal : 0, elliptic->o_maskIdsLocal.p, elliptic->stream);
   }
-  // single rank, persistent TMA-ring axhelm: the mask + gather-scatter run beside the axhelm launch (gs_stream.cu),
-  // chunk by chunk of finished elements, instead of as a second pass after it
-  if (elliptic->streamedGs && oogs->ogs->NhaloGather == 0 && mesh->Nq == 8 && elliptic->Nfields == 1 && axv >= 4 &&
-      mesh->Nelements >= 2 * kNumSMs) {
-    if (!elliptic->gsStream) {
-      elliptic->gsStream.reset(new gs_stream_t());
-      std::vector<dlong> pos(mesh->Nelements);
-      for (dlong e = 0; e < mesh->Nelements; ++e) pos[e] = e;  // o_elementList is the identity
-      if ((rc = elliptic->gsStream->build(oogs->ogs, elliptic->maskIds, pos, mesh->Np,
-                                          std::min<dlong>(kNumSMs, mesh->Nelements))))
-        return rc;
-    }
-    gs_stream_t* G = elliptic->gsStream.get();
-    AxDot extras;
-    AxDot* d = dot ? dot : &extras;
-    d->chunkDone = G->d_done;
-    d->chunkLen = G->chunkLen;
-    d->chunksCounted = false;
-    if ((rc = ellipticAxDot<T>(elliptic, mesh->Nelements, mesh->o_elementList.p, o_q, o_Aq, d))) return rc;
-    if (d->chunksCounted) {
-      ++G->epoch;
-      return gs_stream_launch<T>(G->dev(nm > 0), o_Aq, elliptic->stream);
-    }
-    return oogs->startFinish<T>(o_Aq, elliptic->Nfields, elliptic->fieldOffset, gs_op::add, nm, elliptic->o_maskIds.p,
-                                elliptic->stream);
-  }
   if ((rc = ellipticAxDot<T>(elliptic, mesh->Nelements, mesh->o_elementList.p, o_q, o_Aq, dot))) return rc;
   if (oogs->ogs->NhaloGather) {
     // halo rows are packed from masked values: mask first
@@ -496,7 +470,6 @@ int ellipticSolveSetup(elliptic_t* elliptic)
   // 42.0 vs 39.4 us per operator at E=4096: off unless asked for
   elliptic->fusedGsAx = options.compareArgs("FUSED GS AX", "TRUE") || getenv("NRSB_FUSED_GS") != nullptr;
   elliptic->fusedDotAx = !options.compareArgs("FUSED DOT AX", "FALSE") && getenv("NRSB_NO_FUSED_DOT") == nullptr;
-  elliptic->streamedGs = !options.compareArgs("STREAMED GS", "FALSE") && getenv("NRSB_NO_STREAMED_GS") == nullptr;
   elliptic->overlap = elliptic->ogs->NhaloGather > 0 && !options.compareArgs("ENABLE GS COMM OVERLAP", "FALSE") &&
                       mesh->NlocalGatherElements > 0;
 

@@ -23,52 +23,131 @@
 
 namespace nrsb {
 
-// kRPT rows per thread.  All value loads of all rows of a thread are issued (predicated, no branches) before
-// the first add, so a thread has up to 8 kRPT independent loads in flight.  Copies are summed in ascending
-// local index, as the reference's CSR loop does (bit-identical sums).
+// One block = one row kind (pairs / quads / octets / general / masked nodes), chosen by blockIdx.x, so a block has
+// no divergence and every thread holds only what its kind needs: kRP pair rows per thread are 2 kRP index words and
+// 2 kRP values, all loads of a thread issued before the first add (predicated, no branches).  The grid is sized to
+// fit ONE wave of 2048 threads per SM (16 blocks of 128 threads at 32 registers): the second wave of the
+// one-row-per-thread kernel cost a second round of  index load -> value load -> store  latencies (11.7 us -> see
+// profiles/ for the E = 4096 numbers).  Copies are summed in ascending local index, as the reference's CSR loop does
+// (bit-identical sums).
 // The kernel is launched as a programmatic dependent launch: blocks may become resident while the producer
 // (axhelm) is still running, fetch their index entries, and sleep in pdl_wait() until its stores are visible.
-template <typename T, int kRPT, int kBS>
-__global__ void __launch_bounds__(kBS, kRPT == 1 ? 2048 / kBS : 1)  // 1 row per thread: 32 registers, 2048 threads per SM
-    gs_rows_kernel(const GsRowsDev R, const int Nfields, const dlong stride, T* __restrict__ q)
+struct GsGrid {
+  int pairBlocks, quadBlocks, octBlocks, genBlocks, maskBlocks;
+};
+constexpr int kGsBS = 128;
+constexpr int kGsMaskPerThread = 4;
+
+template <typename T, int kRP>
+__global__ void __launch_bounds__(kGsBS, 2048 / kGsBS)
+    gs_rows_kernel(const GsRowsDev R, const GsGrid G, const dlong stride, T* __restrict__ q)
 {
-  (void)Nfields;
   pdl_trigger();  // a persistent axhelm launch behind this kernel may start its prologue on drained SMs
   T* __restrict__ qf = q + (size_t)blockIdx.y * stride;
-  GsRowRef r[kRPT];
+  int b = blockIdx.x;
+  const int t = threadIdx.x;
+  if (b < G.pairBlocks) {
+    int2 id[kRP];
 #pragma unroll
-  for (int j = 0; j < kRPT; ++j) r[j] = gs_row_fetch(R, ((long)blockIdx.x * kRPT + j) * blockDim.x + threadIdx.x);
-  pdl_wait();
-  T v[kRPT][8];
-#pragma unroll
-  for (int j = 0; j < kRPT; ++j)
-#pragma unroll
-    for (int c = 0; c < 8; ++c) v[j][c] = (c < r[j].n && r[j].n > 1) ? qf[r[j].id[c]] : T(0);
-#pragma unroll
-  for (int j = 0; j < kRPT; ++j) {
-    T s = T(0);
-#pragma unroll
-    for (int c = 0; c < 8; ++c)
-      if (c < r[j].n) s += v[j][c];
-    if (r[j].n == 1) s = T(0);  // masked node
-    if (r[j].n == -1) {
-      for (int c = r[j].id[0]; c < r[j].id[1]; ++c) s += qf[R.genIds[c]];
-      for (int c = r[j].id[0]; c < r[j].id[1]; ++c) qf[R.genIds[c]] = s;
+    for (int j = 0; j < kRP; ++j) {
+      const int r = (b * kRP + j) * kGsBS + t;
+      id[j] = r < R.nPairs ? R.pairs[r] : make_int2(-1, -1);
     }
+    pdl_wait();
+    T a[kRP], c[kRP];
 #pragma unroll
-    for (int c = 0; c < 8; ++c)
-      if (c < r[j].n) qf[r[j].id[c]] = s;
+    for (int j = 0; j < kRP; ++j)
+      if (id[j].x >= 0) {
+        a[j] = qf[id[j].x];
+        c[j] = qf[id[j].y];
+      }
+#pragma unroll
+    for (int j = 0; j < kRP; ++j)
+      if (id[j].x >= 0) {
+        T s = T(0);
+        s += a[j];
+        s += c[j];
+        qf[id[j].x] = s;
+        qf[id[j].y] = s;
+      }
+    return;
   }
-}
-
-int gs_rows_per_thread()
-{
-  static const int rpt = [] {
-    const char* e = getenv("NRSB_GS_RPT");
-    const int v = e ? atoi(e) : 1;
-    return (v == 2 || v == 4) ? v : 1;
-  }();
-  return rpt;
+  b -= G.pairBlocks;
+  if (b < G.quadBlocks) {
+    const int r = b * kGsBS + t;
+    const int4 id = r < R.nQuads ? R.quads[r] : make_int4(-1, -1, -1, -1);
+    pdl_wait();
+    if (id.x < 0) return;
+    const T v0 = qf[id.x], v1 = qf[id.y], v2 = qf[id.z], v3 = qf[id.w];
+    T s = T(0);
+    s += v0;
+    s += v1;
+    s += v2;
+    s += v3;
+    qf[id.x] = s;
+    qf[id.y] = s;
+    qf[id.z] = s;
+    qf[id.w] = s;
+    return;
+  }
+  b -= G.quadBlocks;
+  if (b < G.octBlocks) {
+    const int r = b * kGsBS + t;
+    int4 ia = make_int4(-1, -1, -1, -1), ib = ia;
+    if (r < R.nOcts) {
+      ia = R.octs[2 * r];
+      ib = R.octs[2 * r + 1];
+    }
+    pdl_wait();
+    if (ia.x < 0) return;
+    const T v0 = qf[ia.x], v1 = qf[ia.y], v2 = qf[ia.z], v3 = qf[ia.w];
+    const T v4 = qf[ib.x], v5 = qf[ib.y], v6 = qf[ib.z], v7 = qf[ib.w];
+    T s = T(0);
+    s += v0;
+    s += v1;
+    s += v2;
+    s += v3;
+    s += v4;
+    s += v5;
+    s += v6;
+    s += v7;
+    qf[ia.x] = s;
+    qf[ia.y] = s;
+    qf[ia.z] = s;
+    qf[ia.w] = s;
+    qf[ib.x] = s;
+    qf[ib.y] = s;
+    qf[ib.z] = s;
+    qf[ib.w] = s;
+    return;
+  }
+  b -= G.octBlocks;
+  if (b < G.genBlocks) {
+    const int r = b * kGsBS + t;
+    int s0 = 0, s1 = 0;
+    if (r < R.nGen) {
+      s0 = R.genStarts[r];
+      s1 = R.genStarts[r + 1];
+    }
+    pdl_wait();
+    T s = T(0);
+    for (int c = s0; c < s1; ++c) s += qf[R.genIds[c]];
+    for (int c = s0; c < s1; ++c) qf[R.genIds[c]] = s;
+    return;
+  }
+  b -= G.genBlocks;
+  {
+    int id[kGsMaskPerThread];
+#pragma unroll
+    for (int j = 0; j < kGsMaskPerThread; ++j) {
+      const int r = (b * kGsMaskPerThread + j) * kGsBS + t;
+      id[j] = r < R.nMasked ? R.maskIds[r] : -1;
+    }
+    pdl_wait();
+#pragma unroll
+    for (int j = 0; j < kGsMaskPerThread; ++j)
+      if (id[j] >= 0) qf[id[j]] = T(0);
+  }
 }
 
 template <typename T>
@@ -76,19 +155,25 @@ int gs_rows_launch(const GsRowsDev& R, int Nfields, dlong stride, T* q, cudaStre
 {
   const long total = (long)R.nPairs + R.nQuads + R.nOcts + R.nGen + R.nMasked;
   if (total == 0 || Nfields == 0) return NRSB_OK;
-  const int rpt = gs_rows_per_thread();
-  static const int bs = [] {
-    const char* e = getenv("NRSB_GS_BS");
-    const int v = e ? atoi(e) : 128;  // measured (tools/gs_timing.py): 64: 12.35, 128: 11.7-12.3, 256: 12.35, 512: 13.7, 1024: 17.4 us
-    return (v == 64 || v == 256 || v == 512 || v == 1024) ? v : 128;
-  }();
-  const long perBlock = (long)bs * rpt;
-  dim3 grid((unsigned)((total + perBlock - 1) / perBlock), Nfields);
-  auto kern = rpt == 1 ? (bs == 64 ? gs_rows_kernel<T, 1, 64> : bs == 128 ? gs_rows_kernel<T, 1, 128>
-                                    : (bs == 512 ? gs_rows_kernel<T, 1, 512>
-                                                 : (bs == 1024 ? gs_rows_kernel<T, 1, 1024> : gs_rows_kernel<T, 1, 256>)))
-                       : (rpt == 2 ? gs_rows_kernel<T, 2, 256> : gs_rows_kernel<T, 4, 256>);
-  NRSB_CUDA(launch_pdl_consumer(kern, grid, dim3(rpt == 1 ? bs : 256), 0, stream, R, Nfields, stride, q));
+  auto blocks = [](long n, long per) { return (int)((n + per - 1) / per); };
+  GsGrid G;
+  G.quadBlocks = blocks(R.nQuads, kGsBS);
+  G.octBlocks = blocks(R.nOcts, kGsBS);
+  G.genBlocks = blocks(R.nGen, kGsBS);
+  G.maskBlocks = blocks(R.nMasked, (long)kGsBS * kGsMaskPerThread);
+  // pair rows per thread: the smallest of 1..3 (fp32: 1..4) that keeps the whole grid within one wave (NRSB_GS_RPT forces it)
+  static const int forced = getenv("NRSB_GS_RPT") ? atoi(getenv("NRSB_GS_RPT")) : 0;
+  const long wave = (long)kNumSMs * (2048 / kGsBS);
+  int rp = 1;
+  const long others = (long)(G.quadBlocks + G.octBlocks + G.genBlocks + G.maskBlocks) * Nfields;
+  const int rpMax = sizeof(T) == 8 ? 3 : 4;  // fp64: 4 pair rows per thread do not fit 32 registers
+  while (rp < rpMax && (long)blocks(R.nPairs, (long)kGsBS * rp) * Nfields + others > wave) ++rp;
+  if (forced >= 1 && forced <= rpMax) rp = forced;
+  G.pairBlocks = blocks(R.nPairs, (long)kGsBS * rp);
+  dim3 grid((unsigned)(G.pairBlocks + G.quadBlocks + G.octBlocks + G.genBlocks + G.maskBlocks), Nfields);
+  auto kern = rp == 1 ? gs_rows_kernel<T, 1> : rp == 2 ? gs_rows_kernel<T, 2> : rp == 3 ? gs_rows_kernel<T, 3>
+                                                                                       : gs_rows_kernel<T, 4>;
+  NRSB_CUDA(launch_pdl_consumer(kern, grid, dim3(kGsBS), 0, stream, R, G, stride, q));
   return NRSB_OK;
 }
 template int gs_rows_launch<double>(const GsRowsDev&, int, dlong, double*, cudaStream_t);

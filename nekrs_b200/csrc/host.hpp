@@ -319,9 +319,6 @@ class elliptic_t {
   bool fusedDotAx = true;
   dbuf<double> o_dotPartials;
   unsigned long long fusedArriveTarget = 0;
-  // mask + on-rank gather-scatter by a co-resident kernel WHILE the persistent axhelm launch runs (gs_stream.cu)
-  bool streamedGs = true;
-  std::unique_ptr<gs_stream_t> gsStream;
   dlong Nmasked = 0, NmaskedLocal = 0, NmaskedGlobal = 0;
   dbuf<dlong> o_maskIds, o_maskIdsLocal, o_maskIdsGlobal;
   std::vector<dlong> maskIds;

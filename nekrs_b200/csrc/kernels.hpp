@@ -10,13 +10,6 @@ namespace nrsb {
 struct AxDot {
   double* partials = nullptr;
   int n = 0;
-  // streamed gather-scatter (gs_stream.cu): when set, the persistent axhelm launch counts every finished element of
-  // list positions [c * chunkLen, (c+1) * chunkLen) into chunkDone[c] (fence + device-scope add after the element's
-  // stores), so that a co-resident kernel can gather-scatter the rows of finished chunks while the launch runs on.
-  // Honoured by the TMA-ring variants only; `chunksCounted` tells the caller whether it was.
-  unsigned long long* chunkDone = nullptr;
-  int chunkLen = 0;
-  bool chunksCounted = false;
 };
 template <typename T>
 int ax_launch(int Nq, int variant, dlong Nelements, dlong loffset, const dlong* elementList, const T* ggeo,

@@ -3,7 +3,7 @@ E = 20^3 = 8000 at N = 7, against the oracle on the full mesh, through the C ABI
 
 Why a separate file: with <= 148 elements every CTA of the persistent TMA-ring axhelm handles ONE element, so
 consumer groups 1..2, the ring wrap (i >= NSTAGES), the mbarrier phase flips, the empty[] hand-back, the
-per-CTA q^T A q partials and (streamed gather-scatter) the chunk counters never execute.  Here each CTA
+per-CTA q^T A q partials never execute.  Here each CTA
 processes 27-55 elements (same check benchmarkAx.cpp:289-305 does at bench size: every variant against the
 first, 400 eps).
 
@@ -69,13 +69,11 @@ def test_fullsize_ax_and_operator_fp64(full, variant):
 
 def test_fullsize_operator_paths_bit_identical(full):
     """The gather-scatter sums every row in the reference's order (ascending local index), whichever launch
-    structure executes it: two launches, phase 2 of the axhelm launch, or the streamed gather-scatter that runs
-    next to the axhelm launch.  Same Ax variant => same bits."""
+    structure executes it: two launches or phase 2 of the axhelm launch.  Same Ax variant => same bits."""
     mesh, ell, n = full["mesh"], full["ell"], full["n"]
     d_q = DB(like=padded(full["q"], ell.fieldOffset))
     outs = {}
-    for name, extra in (("two-launch", {"STREAMED GS": "FALSE"}), ("in-launch", {"FUSED GS AX": "TRUE"}),
-                        ("streamed", {"STREAMED GS": "TRUE"})):
+    for name, extra in (("two-launch", {}), ("in-launch", {"FUSED GS AX": "TRUE"})):
         e2 = Elliptic(mesh, dict(OPTS, **extra))
         e2.set_ax_variant(8, 5)
         d = DB.zeros(e2.fieldOffset, np.float64)
@@ -86,7 +84,7 @@ def test_fullsize_operator_paths_bit_identical(full):
         outs[name + "/unmasked"] = d.download()[:n].copy()
         e2.destroy()
     assert relerr(outs["two-launch"], full["out_ref"]) < 1e-12
-    for k in ("in-launch", "streamed"):
+    for k in ("in-launch",):
         assert np.array_equal(outs[k], outs["two-launch"]), k
         assert np.array_equal(outs[k + "/unmasked"], outs["two-launch/unmasked"]), k
 
