@@ -349,6 +349,17 @@ def run_ours(args):
     clocks = sampler.stop() if sampler else None
     e2e_ms_mean = float(np.mean(e2e_ms))
 
+    # ---- the other half of BASELINE.json's metric: kershaw BP5 (PCG, fixed work) and BPS5 (p-multigrid FGMRES) at
+    #      20^3 elements per GPU, kershaw.udf's protocol (warm-up solve, timed solve, min over repetitions)
+    kershaw = None
+    if not args.no_kershaw:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        from kershaw_bench import run_kershaw
+        try:
+            kershaw = run_kershaw(dist, rank, world, local_rank, n=20, N=N, reps=3, comm=bench.comm)
+        except Exception as e:  # the headline line must not be lost to a failure here
+            kershaw = {"error": repr(e)}
+
     if dist is not None:
         import torch
         t = torch.tensor([ms_per_step, ms_ax, e2e_ms_mean, e2e_pipe_ms], device="cuda", dtype=torch.float64)
@@ -394,6 +405,7 @@ def run_ours(args):
                                   "api": "nrsb_elliptic_operator_host (one blocking call per step)"}},
         "parity_relerr": parity, "parity": "fused operator on this mesh vs oracle (whole mesh, every rank its brick), "
                                             "3 consecutive applications, max over ranks; gate 1e-12",
+        "kershaw": kershaw,
         "gpu_launches": args.steps * bench.launches_per_step,
         "clocks": clocks, "wall_s": wall,
     }
@@ -412,6 +424,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-kershaw", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -93,6 +93,31 @@ int nrsb_axpbyMany(int precision, nrsb_dlong N, int Nfields, nrsb_dlong offset, 
                    double beta, void* d_y, void* stream);
 int nrsb_axmyz(int precision, nrsb_dlong N, double alpha, const void* d_x, const void* d_y, void* d_z, void* stream);
 int nrsb_scale(int precision, nrsb_dlong N, double alpha, void* d_x, void* stream);
+/* the rest of the family the elliptic path and its callers use (linAlg.hpp:70-142): a *= alpha per field,
+ * a += alpha, |a|, y = alpha x y (axmy / paxmy; Many: mode 1 x per field, mode 0 one x for all fields),
+ * z = alpha x y per field (axmyzMany / paxmyzMany), y = alpha / y (ady / adyMany / padyMany), y = alpha x / y,
+ * z = alpha x + beta y per field (axpbyzMany) */
+int nrsb_scaleMany(int precision, nrsb_dlong N, int Nfields, nrsb_dlong fieldOffset, double alpha, void* d_a,
+                   void* stream);
+int nrsb_add(int precision, nrsb_dlong N, double alpha, void* d_a, void* stream);
+int nrsb_abs(int precision, nrsb_dlong N, void* d_a, void* stream);
+int nrsb_axmy(int precision, nrsb_dlong N, double alpha, const void* d_x, void* d_y, void* stream);
+int nrsb_axmyMany(int precision, nrsb_dlong N, int Nfields, nrsb_dlong offset, int mode, double alpha, const void* d_x,
+                  void* d_y, void* stream);
+int nrsb_axmyzMany(int precision, nrsb_dlong N, int Nfields, nrsb_dlong offset, double alpha, const void* d_x,
+                   const void* d_y, void* d_z, void* stream);
+int nrsb_adyMany(int precision, nrsb_dlong N, int Nfields, nrsb_dlong offset, double alpha, void* d_y, void* stream);
+int nrsb_axdy(int precision, nrsb_dlong N, double alpha, const void* d_x, void* d_y, void* stream);
+int nrsb_axpbyzMany(int precision, nrsb_dlong N, int Nfields, nrsb_dlong offset, double alpha, const void* d_x,
+                    double beta, const void* d_y, void* d_z, void* stream);
+/* ellipticBlockBuildDiagonalHex3D (kernels/elliptic/ellipticBlockBuildDiagonalHex3D.okl; ellipticUpdateJacobi.cpp:
+ * 38-47,66-75): Aq[id + l*offset] = diag(D^T lambda0 G D)[id] (+ lambda1 GwJ), l < Nfields.  lambdaField = 1:
+ * lambda0/lambda1 are per-node fields read at id + l*loffset (the reference's layout), 0: one value each.
+ * D_host: HOST, row-major D[i][m] in the precision of the call. */
+int nrsb_ellipticBlockBuildDiagonalHex3D(int Nq, int precision, nrsb_dlong Nelements, int Nfields, nrsb_dlong offset,
+                                         nrsb_dlong loffset, const void* d_ggeo, const void* D_host,
+                                         const void* d_lambda0, const void* d_lambda1, int poisson, int lambdaField,
+                                         void* d_Aq, void* stream);
 int nrsb_copyDfloatToPfloat(nrsb_dlong N, const double* d_x, float* d_y, void* stream);
 int nrsb_copyPfloatToDfloat(nrsb_dlong N, const float* d_x, double* d_y, void* stream);
 /* reductions return the (rank-local) value to the host: they synchronise the stream. */
@@ -264,6 +289,15 @@ int nrsb_elliptic_get_real(nrsb_elliptic_t h, const char* key, double* value);
  * "level<k>:invDegree", "level<k>:maskIds", "level<k>:Sx|Sy|Sz|invL|wts" (float) ; returns count */
 int nrsb_elliptic_get_array(nrsb_elliptic_t h, const char* key, void* out_host, int64_t capacity, int64_t* count);
 int nrsb_elliptic_set_option(nrsb_elliptic_t h, const char* key, const char* value); /* before re-setup of precon */
+/* variable coefficients (ELLIPTIC COEFF FIELD; p_lambda = 1 in ellipticPartialAxCoeffHex3D.okl): per-node lambda0 /
+ * lambda1 (device, fp64, caller-owned like the reference's o_lambda0 / o_lambda1).  Refreshes the multigrid levels'
+ * copies (ellipticMultiGridUpdateLambda, MG/ellipticMultiGridUpdateLambda.cpp) and the inverse diagonals
+ * (ellipticUpdateJacobi, ellipticUpdateJacobi.cpp:87-115).  With the option ELLIPTIC PRECO COEFF FIELD = TRUE both
+ * refreshes also run at the top of every nrsb_elliptic_solve (ellipticSolve.cpp:79-88). */
+int nrsb_elliptic_set_coeff_field(nrsb_elliptic_t h, const double* d_lambda0, const double* d_lambda1);
+int nrsb_elliptic_set_coefficients(nrsb_elliptic_t h, double lambda0, double lambda1); /* constant coefficients */
+int nrsb_elliptic_update_jacobi(nrsb_elliptic_t h);  /* ellipticUpdateJacobi(elliptic) */
+int nrsb_elliptic_update_lambda(nrsb_elliptic_t h);  /* ellipticMultiGridUpdateLambda(elliptic) */
 int nrsb_elliptic_set_ax_variant(nrsb_elliptic_t h, int precision, int variant);
 int nrsb_elliptic_set_stream(nrsb_elliptic_t h, void* stream);
 /* kernel-variant autotuning as in benchmarkAx (src/bench/axHelm/benchmarkAx.cpp:140-146,289-305) */

@@ -309,6 +309,84 @@ int nrsb_scale(int precision, nrsb_dlong N, double alpha, void* d_x, void* strea
   return precision == 8 ? scale_launch<double>(N, alpha, (double*)d_x, ST(stream))
                         : scale_launch<float>(N, (float)alpha, (float*)d_x, ST(stream));
 }
+int nrsb_scaleMany(int precision, nrsb_dlong N, int Nfields, nrsb_dlong fieldOffset, double alpha, void* d_a,
+                   void* stream)
+{
+  PREC_OK(precision);
+  return precision == 8 ? scale_many_launch<double>(N, Nfields, fieldOffset, alpha, (double*)d_a, ST(stream))
+                        : scale_many_launch<float>(N, Nfields, fieldOffset, (float)alpha, (float*)d_a, ST(stream));
+}
+int nrsb_add(int precision, nrsb_dlong N, double alpha, void* d_a, void* stream)
+{
+  PREC_OK(precision);
+  return precision == 8 ? add_scalar_launch<double>(N, DevScalar::host(alpha), (double*)d_a, ST(stream))
+                        : add_scalar_launch<float>(N, DevScalar::host(alpha), (float*)d_a, ST(stream));
+}
+int nrsb_abs(int precision, nrsb_dlong N, void* d_a, void* stream)
+{
+  PREC_OK(precision);
+  return precision == 8 ? abs_launch<double>(N, (double*)d_a, ST(stream)) : abs_launch<float>(N, (float*)d_a, ST(stream));
+}
+int nrsb_axmy(int precision, nrsb_dlong N, double alpha, const void* d_x, void* d_y, void* stream)
+{
+  PREC_OK(precision);
+  return precision == 8 ? axmy_many_launch<double>(N, 1, 0, 1, alpha, (const double*)d_x, (double*)d_y, ST(stream))
+                        : axmy_many_launch<float>(N, 1, 0, 1, (float)alpha, (const float*)d_x, (float*)d_y, ST(stream));
+}
+int nrsb_axmyMany(int precision, nrsb_dlong N, int Nfields, nrsb_dlong offset, int mode, double alpha, const void* d_x,
+                  void* d_y, void* stream)
+{
+  PREC_OK(precision);
+  return precision == 8
+             ? axmy_many_launch<double>(N, Nfields, offset, mode, alpha, (const double*)d_x, (double*)d_y, ST(stream))
+             : axmy_many_launch<float>(N, Nfields, offset, mode, (float)alpha, (const float*)d_x, (float*)d_y, ST(stream));
+}
+int nrsb_axmyzMany(int precision, nrsb_dlong N, int Nfields, nrsb_dlong offset, double alpha, const void* d_x,
+                   const void* d_y, void* d_z, void* stream)
+{
+  PREC_OK(precision);
+  return precision == 8 ? axmyz_many_launch<double>(N, Nfields, offset, alpha, (const double*)d_x, (const double*)d_y,
+                                                    (double*)d_z, ST(stream))
+                        : axmyz_many_launch<float>(N, Nfields, offset, (float)alpha, (const float*)d_x,
+                                                   (const float*)d_y, (float*)d_z, ST(stream));
+}
+int nrsb_adyMany(int precision, nrsb_dlong N, int Nfields, nrsb_dlong offset, double alpha, void* d_y, void* stream)
+{
+  PREC_OK(precision);
+  return precision == 8 ? ady_many_launch<double>(N, Nfields, offset, alpha, (double*)d_y, ST(stream))
+                        : ady_many_launch<float>(N, Nfields, offset, (float)alpha, (float*)d_y, ST(stream));
+}
+int nrsb_axdy(int precision, nrsb_dlong N, double alpha, const void* d_x, void* d_y, void* stream)
+{
+  PREC_OK(precision);
+  return precision == 8 ? axdy_launch<double>(N, alpha, (const double*)d_x, (double*)d_y, ST(stream))
+                        : axdy_launch<float>(N, (float)alpha, (const float*)d_x, (float*)d_y, ST(stream));
+}
+int nrsb_axpbyzMany(int precision, nrsb_dlong N, int Nfields, nrsb_dlong offset, double alpha, const void* d_x,
+                    double beta, const void* d_y, void* d_z, void* stream)
+{
+  PREC_OK(precision);
+  return precision == 8 ? axpbyz_many_launch<double>(N, Nfields, offset, alpha, (const double*)d_x, beta,
+                                                     (const double*)d_y, (double*)d_z, ST(stream))
+                        : axpbyz_many_launch<float>(N, Nfields, offset, (float)alpha, (const float*)d_x, (float)beta,
+                                                    (const float*)d_y, (float*)d_z, ST(stream));
+}
+int nrsb_ellipticBlockBuildDiagonalHex3D(int Nq, int precision, nrsb_dlong Nelements, int Nfields, nrsb_dlong offset,
+                                         nrsb_dlong loffset, const void* d_ggeo, const void* D_host,
+                                         const void* d_lambda0, const void* d_lambda1, int poisson, int lambdaField,
+                                         void* d_Aq, void* stream)
+{
+  PREC_OK(precision);
+  NRSB_REQUIRE(D_host && (Nelements == 0 || (d_ggeo && d_lambda0 && d_Aq)), "NULL argument");
+  NRSB_REQUIRE(poisson || d_lambda1, "lambda1 is NULL for a Helmholtz operator");
+  return precision == 8
+             ? build_diagonal_launch<double>(Nq, Nelements, Nfields, offset, loffset, (const double*)d_ggeo,
+                                             (const double*)D_host, (const double*)d_lambda0, (const double*)d_lambda1,
+                                             poisson, lambdaField, (double*)d_Aq, ST(stream))
+             : build_diagonal_launch<float>(Nq, Nelements, Nfields, offset, loffset, (const float*)d_ggeo,
+                                            (const float*)D_host, (const float*)d_lambda0, (const float*)d_lambda1,
+                                            poisson, lambdaField, (float*)d_Aq, ST(stream));
+}
 int nrsb_copyDfloatToPfloat(nrsb_dlong N, const double* d_x, float* d_y, void* stream)
 {
   return copy_d2f_launch(N, d_x, d_y, ST(stream));

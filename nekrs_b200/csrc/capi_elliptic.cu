@@ -532,11 +532,16 @@ int nrsb_elliptic_get_array(nrsb_elliptic_t h, const char* key, void* out_host, 
     if (name == "Sz") return out_dev(L->o_Sz.p, L->o_Sz.n, out_host, capacity, count);
     if (name == "invL") return out_dev(L->o_invL.p, L->o_invL.n, out_host, capacity, count);
     if (name == "wts") return out_dev(L->o_wts.p, L->o_wts.n, out_host, capacity, count);
+    if (name == "invDiagA") return out_dev(L->o_invDiagA.p, L->o_invDiagA.n, out_host, capacity, count);
+    if (name == "lambda0Field")
+      return out_dev(L->elliptic->o_lambda0FieldPfloat.p, L->elliptic->o_lambda0FieldPfloat.n, out_host, capacity, count);
     if (name == "x") return out_vec(L->mesh->x, out_host, capacity, count);
     if (name == "ggeoPfloat") return out_dev(L->mesh->o_ggeoPfloat.p, L->mesh->o_ggeoPfloat.n, out_host, capacity, count);
     set_last_error("unknown key " + k);
     return NRSB_ERR_INVALID;
   }
+  if (k == "invDiagA" && e.precon && e.precon->o_invDiagA.p)
+    return out_dev(e.precon->o_invDiagA.p, (size_t)e.mesh->Nlocal, out_host, capacity, count);
   if (k == "maskIds") return out_vec(e.maskIds, out_host, capacity, count);
   if (k == "invDegree") return out_vec(e.ogs->invDegree, out_host, capacity, count);
   if (k == "meshInvDegree") return out_vec(e.mesh->ogs->invDegree, out_host, capacity, count);
@@ -559,6 +564,48 @@ int nrsb_elliptic_set_option(nrsb_elliptic_t h, const char* key, const char* val
   if (k == "PRECONDITIONER") return ellipticPreconditionerSetup(&h->impl);
   if (k == "SOLVER" || k == "PGMRES RESTART") return ellipticKrylovWorkspace(&h->impl);
   return NRSB_OK;
+}
+
+/* ELLIPTIC COEFF FIELD: per-node coefficients (device, fp64, caller-owned, Nlocal entries each; lambda1 may be
+ * NULL for a Poisson handle).  NULL lambda0 returns to the constant coefficients of the setup. */
+int nrsb_elliptic_set_coeff_field(nrsb_elliptic_t h, const double* d_lambda0, const double* d_lambda1)
+{
+  NRSB_REQUIRE(h, "handle is NULL");
+  return ellipticSetCoeffField(&h->impl, d_lambda0, d_lambda1);
+}
+/* constant coefficients changed (e.g. lambda1 = rho / dt of the velocity solve): device scalars of the solver and
+ * of every multigrid level, then the inverse diagonals */
+int nrsb_elliptic_set_coefficients(nrsb_elliptic_t h, double lambda0, double lambda1)
+{
+  NRSB_REQUIRE(h, "handle is NULL");
+  auto set = [&](elliptic_t* e) -> int {
+    e->lambda0Value = lambda0;
+    e->lambda1Value = lambda1;
+    const double d[2] = {lambda0, lambda1};
+    const float f[2] = {(float)lambda0, (float)lambda1};
+    if (e->o_lambda0.p) NRSB_CUDA(cudaMemcpyAsync(e->o_lambda0.p, d, sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    if (e->o_lambda1.p) NRSB_CUDA(cudaMemcpyAsync(e->o_lambda1.p, d + 1, sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    if (e->o_lambda0Pfloat.p) NRSB_CUDA(cudaMemcpyAsync(e->o_lambda0Pfloat.p, f, sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    if (e->o_lambda1Pfloat.p) NRSB_CUDA(cudaMemcpyAsync(e->o_lambda1Pfloat.p, f + 1, sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    NRSB_CUDA(cudaStreamSynchronize(e->stream));  // the host copies above live on this stack frame
+    return NRSB_OK;
+  };
+  int rc;
+  if ((rc = set(&h->impl))) return rc;
+  if (h->impl.precon && h->impl.precon->MGSolver)
+    for (auto& e : h->impl.precon->MGSolver->ellipticLevels)
+      if ((rc = set(e.get()))) return rc;
+  return ellipticUpdateJacobi(&h->impl);
+}
+int nrsb_elliptic_update_jacobi(nrsb_elliptic_t h)
+{
+  NRSB_REQUIRE(h, "handle is NULL");
+  return ellipticUpdateJacobi(&h->impl);
+}
+int nrsb_elliptic_update_lambda(nrsb_elliptic_t h)
+{
+  NRSB_REQUIRE(h, "handle is NULL");
+  return ellipticMultiGridUpdateLambda(&h->impl);
 }
 
 int nrsb_elliptic_set_ax_variant(nrsb_elliptic_t h, int precision, int variant)

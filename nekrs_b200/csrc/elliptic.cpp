@@ -128,8 +128,8 @@ template <>
 struct prec_traits<double> {
   static const double* ggeo(mesh_t* m) { return m->o_ggeo.p; }
   static const double* D(mesh_t* m) { return m->D.data(); }
-  static const double* lambda0(elliptic_t* e) { return e->o_lambda0.p; }
-  static const double* lambda1(elliptic_t* e) { return e->o_lambda1.p; }
+  static const double* lambda0(elliptic_t* e) { return e->lambdaField ? e->o_lambda0Field : e->o_lambda0.p; }
+  static const double* lambda1(elliptic_t* e) { return e->lambdaField ? e->o_lambda1Field : e->o_lambda1.p; }
   static const double* invDegree(elliptic_t* e) { return e->o_invDegree; }
   static constexpr int idx = 0;
 };
@@ -137,8 +137,8 @@ template <>
 struct prec_traits<float> {
   static const float* ggeo(mesh_t* m) { return m->o_ggeoPfloat.p; }
   static const float* D(mesh_t* m) { return m->Dpfloat.data(); }
-  static const float* lambda0(elliptic_t* e) { return e->o_lambda0Pfloat.p; }
-  static const float* lambda1(elliptic_t* e) { return e->o_lambda1Pfloat.p; }
+  static const float* lambda0(elliptic_t* e) { return e->lambdaField ? e->o_lambda0FieldPfloat.p : e->o_lambda0Pfloat.p; }
+  static const float* lambda1(elliptic_t* e) { return e->lambdaField ? e->o_lambda1FieldPfloat.p : e->o_lambda1Pfloat.p; }
   static const float* invDegree(elliptic_t* e) { return e->o_invDegreePfloat; }
   static constexpr int idx = 1;
 };
@@ -155,8 +155,8 @@ static int ellipticAxDot(elliptic_t* elliptic, dlong NelementsList, const dlong*
   int variant = elliptic->ax_variant[P::idx];
   if (variant < 0) variant = ax_default_variant(mesh->Nq, (int)sizeof(T));
   return ax_launch<T>(mesh->Nq, variant, NelementsList, elliptic->loffset, o_elementList, P::ggeo(mesh), P::D(mesh),
-                      P::lambda0(elliptic), P::lambda1(elliptic), elliptic->poisson ? 1 : 0, 0, o_q, o_Aq,
-                      elliptic->stream, dot);
+                      P::lambda0(elliptic), P::lambda1(elliptic), elliptic->poisson ? 1 : 0, elliptic->lambdaField ? 1 : 0,
+                      o_q, o_Aq, elliptic->stream, dot);
 }
 
 template <typename T>
@@ -169,8 +169,8 @@ int ellipticAx(elliptic_t* elliptic, dlong NelementsList, const dlong* o_element
   int variant = elliptic->ax_variant[P::idx];
   if (variant < 0) variant = ax_default_variant(mesh->Nq, (int)sizeof(T));
   return ax_launch<T>(mesh->Nq, variant, NelementsList, elliptic->loffset, o_elementList, P::ggeo(mesh), P::D(mesh),
-                      P::lambda0(elliptic), P::lambda1(elliptic), elliptic->poisson ? 1 : 0, 0, o_q, o_Aq,
-                      elliptic->stream);
+                      P::lambda0(elliptic), P::lambda1(elliptic), elliptic->poisson ? 1 : 0, elliptic->lambdaField ? 1 : 0,
+                      o_q, o_Aq, elliptic->stream);
 }
 template int ellipticAx<double>(elliptic_t*, dlong, const dlong*, const double*, double*);
 template int ellipticAx<float>(elliptic_t*, dlong, const dlong*, const float*, float*);
@@ -197,7 +197,8 @@ int ellipticOperator(elliptic_t* elliptic, const T* o_q, T* o_Aq, bool masked, A
   using P = prec_traits<T>;
   const int axv = elliptic->ax_variant[P::idx] < 0 ? ax_default_variant(mesh->Nq, (int)sizeof(T))
                                                    : elliptic->ax_variant[P::idx];
-  const bool gsInLaunch = elliptic->fusedGsAx && elliptic->poisson && mesh->Nq == 8 && elliptic->Nfields == 1 && axv >= 4;
+  const bool gsInLaunch = elliptic->fusedGsAx && elliptic->poisson && !elliptic->lambdaField && mesh->Nq == 8 &&
+                          elliptic->Nfields == 1 && axv >= 4;
   FusedRows FR;
   if (gsInLaunch) {
     if (!elliptic->fusedArrive.p) {
@@ -219,7 +220,8 @@ int ellipticOperator(elliptic_t* elliptic, const T* o_q, T* o_Aq, bool masked, A
     return rc;
   }
   // (the fused launches use the 6-stage ring, which has no room for the Helmholtz GwJ plane: Poisson only)
-  if (elliptic->overlap && elliptic->fusedHaloAx && elliptic->poisson && mesh->Nq == 8 && elliptic->Nfields == 1 &&
+  if (elliptic->overlap && elliptic->fusedHaloAx && elliptic->poisson && !elliptic->lambdaField && mesh->Nq == 8 &&
+      elliptic->Nfields == 1 &&
       elliptic->ax_variant[P::idx] != 0 && mesh->NglobalGatherElements > 0 && oogs->peers.size() <= 32) {
     // ONE launch: Ax over [halo elements, interior elements]; the last F.nPush CTAs of the grid do no element work,
     // they push the halo partial sums over NVLink as soon as the halo elements are stored (oogs::begin_fused sizes
@@ -314,58 +316,118 @@ int ellipticZeroMean(elliptic_t* elliptic, double* o_q)
   return add_scalar_launch<double>(mesh->Nlocal, a, o_q, elliptic->stream);
 }
 
-// diag(A) (ellipticBlockBuildDiagonalHex3D.okl) is formed by probing-free assembly on the host of the
-// element diagonals from ggeo and D, then gather-scattered and inverted (ellipticUpdateJacobi).
+// ellipticUpdateJacobi(elliptic, o_invDiagA) (ellipticUpdateJacobi.cpp:32-85): element diagonals on the device
+// (diag.cu = ellipticBlockBuildDiagonalHex3D), gather-scatter, adyMany / padyMany.
 template <typename T>
 int ellipticBuildDiagonal(elliptic_t* elliptic, T* o_invDiagA)
 {
   mesh_t* mesh = elliptic->mesh;
-  const int Nq = mesh->Nq, Np = mesh->Np;
-  std::vector<float> gf;
-  std::vector<double> gd;
-  const bool useD = mesh->o_ggeo.p != nullptr;
+  using P = prec_traits<T>;
   int rc;
-  if (useD) {
-    if ((rc = mesh->o_ggeo.download(gd))) return rc;
-  } else {
-    if ((rc = mesh->o_ggeoPfloat.download(gf))) return rc;
-  }
-  auto G = [&](dlong e, int c, int n) -> double {
-    const size_t id = (size_t)e * 7 * Np + (size_t)c * Np + n;
-    return useD ? gd[id] : (double)gf[id];
-  };
-  const std::vector<double>& D = mesh->D;
-  std::vector<T> diag(mesh->Nlocal);
-  const double lam0 = elliptic->lambda0Value, lam1 = elliptic->poisson ? 0.0 : elliptic->lambda1Value;
-  for (dlong e = 0; e < mesh->Nelements; ++e)
-    for (int k = 0; k < Nq; ++k)
-      for (int j = 0; j < Nq; ++j)
-        for (int i = 0; i < Nq; ++i) {
-          const int n = i + j * Nq + k * Nq * Nq;
-          double r = 0;
-          for (int m = 0; m < Nq; ++m) {
-            r += G(e, 0, m + j * Nq + k * Nq * Nq) * D[m * Nq + i] * D[m * Nq + i];  // G00
-            r += G(e, 2, i + m * Nq + k * Nq * Nq) * D[m * Nq + j] * D[m * Nq + j];  // G11
-            r += G(e, 5, i + j * Nq + m * Nq * Nq) * D[m * Nq + k] * D[m * Nq + k];  // G22
-          }
-          r += 2 * G(e, 1, n) * D[i * Nq + i] * D[j * Nq + j];  // G01
-          r += 2 * G(e, 4, n) * D[i * Nq + i] * D[k * Nq + k];  // G02
-          r += 2 * G(e, 3, n) * D[j * Nq + j] * D[k * Nq + k];  // G12
-          r *= lam0;
-          r += lam1 * G(e, 6, n);
-          diag[(size_t)e * Np + n] = (T)r;
-        }
-  NRSB_CUDA(cudaMemcpy(o_invDiagA, diag.data(), sizeof(T) * mesh->Nlocal, cudaMemcpyHostToDevice));
-  if ((rc = elliptic->oogs->startFinish<T>(o_invDiagA, 1, 0, gs_op::add, 0, nullptr, elliptic->stream))) return rc;
-  // adyMany: a = 1/a ; masked rows (diag untouched by gs) keep their element value
-  NRSB_CUDA(cudaStreamSynchronize(elliptic->stream));
-  NRSB_CUDA(cudaMemcpy(diag.data(), o_invDiagA, sizeof(T) * mesh->Nlocal, cudaMemcpyDeviceToHost));
-  for (auto& v : diag) v = (T)1 / v;
-  NRSB_CUDA(cudaMemcpy(o_invDiagA, diag.data(), sizeof(T) * mesh->Nlocal, cudaMemcpyHostToDevice));
-  return NRSB_OK;
+  const T* ggeo = P::ggeo(mesh);
+  NRSB_REQUIRE(ggeo != nullptr, "geometric factors of the requested precision are not resident");
+  if ((rc = build_diagonal_launch<T>(mesh->Nq, mesh->Nelements, elliptic->Nfields, elliptic->fieldOffset,
+                                     elliptic->loffset, ggeo, P::D(mesh), P::lambda0(elliptic), P::lambda1(elliptic),
+                                     elliptic->poisson ? 1 : 0, elliptic->lambdaField ? 1 : 0, o_invDiagA,
+                                     elliptic->stream)))
+    return rc;
+  if ((rc = elliptic->oogs->startFinish<T>(o_invDiagA, elliptic->Nfields, elliptic->fieldOffset, gs_op::add, 0, nullptr,
+                                           elliptic->stream)))
+    return rc;
+  return ady_many_launch<T>(mesh->Nlocal, elliptic->Nfields, elliptic->fieldOffset, T(1), o_invDiagA, elliptic->stream);
 }
 template int ellipticBuildDiagonal<double>(elliptic_t*, double*);
 template int ellipticBuildDiagonal<float>(elliptic_t*, float*);
+
+// ellipticUpdateJacobi(ellipticBase) (ellipticUpdateJacobi.cpp:87-115): refresh every inverse diagonal that depends
+// on the coefficients -- the smoother diagonals of the multigrid levels (DAMPEDJACOBI) or the Jacobi preconditioner.
+int ellipticUpdateJacobi(elliptic_t* ellipticBase)
+{
+  options_t& options = ellipticBase->options;
+  precon_t* precon = ellipticBase->precon.get();
+  if (!precon) return NRSB_OK;
+  int rc;
+  if (options.compareArgs("PRECONDITIONER", "MULTIGRID") && options.compareArgs("MULTIGRID SMOOTHER", "DAMPEDJACOBI")) {
+    auto& levels = precon->MGSolver->levels;
+    for (size_t k = 0; k < levels.size(); ++k) {
+      pMGLevel* L = levels[k].get();
+      const bool coarsest = (k + 1 == levels.size());
+      if (coarsest && options.compareArgs("MULTIGRID COARSE SOLVE", "TRUE")) continue;
+      if (!L->o_invDiagA.p) continue;
+      if ((rc = ellipticBuildDiagonal<float>(L->elliptic, L->o_invDiagA.p))) return rc;
+    }
+  } else if (options.compareArgs("PRECONDITIONER", "JACOBI")) {
+    if ((rc = ellipticBuildDiagonal<double>(ellipticBase, precon->o_invDiagA.p))) return rc;
+  }
+  return NRSB_OK;
+}
+
+// ellipticMultiGridUpdateLambda (MG/ellipticMultiGridUpdateLambda.cpp): level 0 gets the fp32 cast of the solver's
+// coefficient fields, every coarser level the nodal interpolation (coarsen kernel with the fine->coarse
+// interpolation matrix, ellipticBuildMultigridLevel.cpp:133-146) of the level above.
+int ellipticMultiGridUpdateLambda(elliptic_t* elliptic)
+{
+  if (!elliptic->lambdaField) return NRSB_OK;
+  mesh_t* mesh = elliptic->mesh;
+  cudaStream_t st = elliptic->stream;
+  int rc;
+  // the solver's own fp32 copy (fp32 operator on the solver mesh)
+  if (elliptic->o_lambda0FieldPfloat.n < (size_t)mesh->Nlocal)
+    if ((rc = elliptic->o_lambda0FieldPfloat.alloc(mesh->Nlocal))) return rc;
+  if ((rc = copy_d2f_launch(mesh->Nlocal, elliptic->o_lambda0Field, elliptic->o_lambda0FieldPfloat.p, st))) return rc;
+  if (!elliptic->poisson) {
+    if (elliptic->o_lambda1FieldPfloat.n < (size_t)mesh->Nlocal)
+      if ((rc = elliptic->o_lambda1FieldPfloat.alloc(mesh->Nlocal))) return rc;
+    if ((rc = copy_d2f_launch(mesh->Nlocal, elliptic->o_lambda1Field, elliptic->o_lambda1FieldPfloat.p, st))) return rc;
+  }
+  if (!elliptic->precon || !elliptic->precon->MGSolver) return NRSB_OK;
+  auto& levels = elliptic->precon->MGSolver->levels;
+  for (size_t k = 0; k < levels.size(); ++k) {
+    elliptic_t* e = levels[k]->elliptic;
+    const dlong Nl = e->mesh->Nlocal;
+    if (e->o_lambda0FieldPfloat.n < (size_t)Nl)
+      if ((rc = e->o_lambda0FieldPfloat.alloc(Nl))) return rc;
+    if (!elliptic->poisson && e->o_lambda1FieldPfloat.n < (size_t)Nl)
+      if ((rc = e->o_lambda1FieldPfloat.alloc(Nl))) return rc;
+    if (k == 0) {
+      if ((rc = copy_d2f_launch(Nl, elliptic->o_lambda0Field, e->o_lambda0FieldPfloat.p, st))) return rc;
+      if (!elliptic->poisson)
+        if ((rc = copy_d2f_launch(Nl, elliptic->o_lambda1Field, e->o_lambda1FieldPfloat.p, st))) return rc;
+    } else {
+      elliptic_t* f = levels[k - 1]->elliptic;
+      NRSB_REQUIRE(!e->interpFromFine.empty(), "multigrid level has no fine-to-coarse interpolation matrix");
+      if ((rc = transfer_dispatch(true, f->mesh->Nq, e->mesh->Nq, e->mesh->Nelements, e->interpFromFine.data(),
+                                  f->o_lambda0FieldPfloat.p, e->o_lambda0FieldPfloat.p, st)))
+        return rc;
+      if (!elliptic->poisson)
+        if ((rc = transfer_dispatch(true, f->mesh->Nq, e->mesh->Nq, e->mesh->Nelements, e->interpFromFine.data(),
+                                    f->o_lambda1FieldPfloat.p, e->o_lambda1FieldPfloat.p, st)))
+          return rc;
+    }
+    e->lambdaField = true;
+  }
+  return NRSB_OK;
+}
+
+// ELLIPTIC COEFF FIELD: switch the handle (and its multigrid levels) to per-node coefficients owned by the caller.
+// nullptr, nullptr switches back to the constant coefficients of the setup.
+int ellipticSetCoeffField(elliptic_t* elliptic, const double* o_lambda0, const double* o_lambda1)
+{
+  if (!o_lambda0) {
+    elliptic->lambdaField = false;
+    elliptic->o_lambda0Field = elliptic->o_lambda1Field = nullptr;
+    if (elliptic->precon && elliptic->precon->MGSolver)
+      for (auto& L : elliptic->precon->MGSolver->levels) L->elliptic->lambdaField = false;
+    return ellipticUpdateJacobi(elliptic);
+  }
+  NRSB_REQUIRE(elliptic->poisson || o_lambda1, "lambda1 field is NULL for a Helmholtz operator");
+  elliptic->lambdaField = true;
+  elliptic->o_lambda0Field = o_lambda0;
+  elliptic->o_lambda1Field = o_lambda1;
+  int rc;
+  if ((rc = ellipticMultiGridUpdateLambda(elliptic))) return rc;
+  return ellipticUpdateJacobi(elliptic);
+}
 
 // ------------------------------------------------------------------------------------------
 // setup
@@ -801,6 +863,14 @@ int ellipticSolve(elliptic_t* elliptic, double* o_r, double* o_x)
   elliptic->resNormFactor = 1 / mesh->volume;
   elliptic->resHistory.clear();
   int rc;
+
+  // coefficient fields that change between solves: refresh the preconditioner's copies (ellipticSolve.cpp:79-88)
+  if (options.compareArgs("ELLIPTIC PRECO COEFF FIELD", "TRUE")) {
+    if (options.compareArgs("PRECONDITIONER", "MULTIGRID"))
+      if ((rc = ellipticMultiGridUpdateLambda(elliptic))) return rc;
+    if (options.compareArgs("PRECONDITIONER", "JACOBI") || options.compareArgs("MULTIGRID SMOOTHER", "DAMPEDJACOBI"))
+      if ((rc = ellipticUpdateJacobi(elliptic))) return rc;
+  }
 
   // r = rhs - A x0
   if ((rc = ellipticAx<double>(elliptic, mesh->Nelements, mesh->o_elementList.p, o_x, elliptic->o_Ap.p))) return rc;

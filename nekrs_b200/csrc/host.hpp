@@ -231,8 +231,12 @@ class MGSolver_t {
   std::vector<std::unique_ptr<mesh_t>> meshLevels;
   int baseLevel = 0;
   std::function<int(float* rhs, float* x)> coarseSolve;
+  // MGSOLVER CYCLE = VCYCLE+ADDITIVE (MGSolver.cpp:99-124): all levels smoothed from zero on the restricted
+  // right-hand side, corrections added; only legal without Chebyshev acceleration
+  bool additive = false;
   int Run(float* o_rhs, float* o_x);
   int runVcycle(int k);
+  int runAdditiveVcycle();
 };
 
 // coarse-grid solver stand-in for BoomerAMG: Jacobi-preconditioned CG on the
@@ -305,6 +309,14 @@ class elliptic_t {
   double lambda0Value = 1.0, lambda1Value = 0.0;
   dbuf<double> o_lambda0, o_lambda1;            // scalars (device), fp64 solver
   dbuf<float> o_lambda0Pfloat, o_lambda1Pfloat;  // MG levels
+  // variable coefficients (ELLIPTIC COEFF FIELD, p_lambda = 1): per-node lambda0 / lambda1.  The fp64 fields of the
+  // solver belong to the caller (like the reference's o_lambda0 / o_lambda1 handles); the fp32 copies -- level 0 a
+  // cast, coarser levels interpolated -- are refreshed by ellipticMultiGridUpdateLambda.
+  bool lambdaField = false;
+  const double* o_lambda0Field = nullptr;
+  const double* o_lambda1Field = nullptr;
+  dbuf<float> o_lambda0FieldPfloat, o_lambda1FieldPfloat;
+  std::vector<float> interpFromFine;  // MG level: [Nq][NqFine] nodal interpolation from the next finer level
   std::vector<int> EToB;
   // masked gather-scatter
   std::unique_ptr<ogs_t> ogs;
@@ -381,7 +393,10 @@ int ellipticOgs(mesh_t* mesh, const std::vector<int>& EToB, elliptic_t* elliptic
 int pcg(elliptic_t* elliptic, double* o_r, double* o_x, double tol, int MAXIT, double& rdotr);
 int pgmres(elliptic_t* elliptic, double* o_r, double* o_x, double tol, int MAXIT, double& rdotr);
 template <typename T>
-int ellipticBuildDiagonal(elliptic_t* elliptic, T* o_invDiagA);  // ellipticUpdateJacobi
+int ellipticBuildDiagonal(elliptic_t* elliptic, T* o_invDiagA);  // ellipticUpdateJacobi(elliptic, o_invDiagA)
+int ellipticUpdateJacobi(elliptic_t* ellipticBase);             // ellipticUpdateJacobi.cpp:87-115
+int ellipticMultiGridUpdateLambda(elliptic_t* elliptic);        // MG/ellipticMultiGridUpdateLambda.cpp
+int ellipticSetCoeffField(elliptic_t* elliptic, const double* o_lambda0, const double* o_lambda1);
 // multigrid.cpp
 int ellipticMultiGridSetup(elliptic_t* elliptic, precon_t* precon);
 std::vector<int> determineMGLevels(const options_t& options, int N);

@@ -40,6 +40,11 @@ int post_fdm_launch(int Nq, dlong Nelements, const float* work1, const float* wo
 // transfer.cu
 int transfer_dispatch(bool coarsen, int NqF, int NqC, dlong Nelements, const float* R_host, const float* in,
                       float* out, cudaStream_t stream);
+// diag.cu: ellipticBlockBuildDiagonalHex3D (element diagonal of the Helmholtz operator; D_host row-major [Nq][Nq])
+template <typename T>
+int build_diagonal_launch(int Nq, dlong Nelements, int Nfields, dlong offset, dlong loffset, const T* ggeo,
+                          const T* D_host, const T* lambda0, const T* lambda1, int poisson, int lambdaField, T* Aq,
+                          cudaStream_t stream);
 bool transfer_supported(int NqF, int NqC);
 bool fdm_supported(int Nq);  // extended size Nq + 2 instantiated
 int geometric_factors_launch(int Nq, dlong Nelements, const double* d_D, const double* d_gllw, const double* x,

@@ -84,6 +84,60 @@ int scale_launch(long N, T a, T* x, cudaStream_t s)
 {
   return ew_launch(N, [=] __device__(long i) { x[i] *= a; }, s);
 }
+// ---- the "Many" family (linAlg.hpp:75-139): Nfields vectors of N entries, `offset` apart, in ONE launch.
+//      The index runs over N * Nfields; field-major so that consecutive threads touch consecutive addresses.
+template <typename F>
+static int ew_many_launch(long N, int Nfields, F f, cudaStream_t s)
+{
+  if (N <= 0 || Nfields <= 0) return NRSB_OK;
+  return ew_launch(N * Nfields, [=] __device__(long g) { f(g % N, (int)(g / N)); }, s);
+}
+template <typename T>
+int scale_many_launch(long N, int Nfields, long offset, T a, T* x, cudaStream_t s)
+{
+  return ew_many_launch(N, Nfields, [=] __device__(long i, int fld) { x[i + fld * offset] *= a; }, s);
+}
+// mode 1: y[n,fld] = a x[n,fld] y[n,fld] ; mode 0: y[n,fld] = a x[n] y[n,fld]   (linAlg.hpp:106-113)
+template <typename T>
+int axmy_many_launch(long N, int Nfields, long offset, int mode, T a, const T* x, T* y, cudaStream_t s)
+{
+  return ew_many_launch(
+      N, Nfields,
+      [=] __device__(long i, int fld) { y[i + fld * offset] = a * x[i + (mode ? fld * offset : 0)] * y[i + fld * offset]; },
+      s);
+}
+template <typename T>
+int axmyz_many_launch(long N, int Nfields, long offset, T a, const T* x, const T* y, T* z, cudaStream_t s)
+{
+  return ew_many_launch(
+      N, Nfields, [=] __device__(long i, int fld) { z[i + fld * offset] = a * x[i + fld * offset] * y[i + fld * offset]; },
+      s);
+}
+// y = a / y  (ady / adyMany / padyMany, linAlg.hpp:133-139)
+template <typename T>
+int ady_many_launch(long N, int Nfields, long offset, T a, T* y, cudaStream_t s)
+{
+  return ew_many_launch(N, Nfields, [=] __device__(long i, int fld) { y[i + fld * offset] = a / y[i + fld * offset]; }, s);
+}
+// y = a x / y  (axdy, linAlg.hpp:141-142)
+template <typename T>
+int axdy_launch(long N, T a, const T* x, T* y, cudaStream_t s)
+{
+  return ew_launch(N, [=] __device__(long i) { y[i] = a * x[i] / y[i]; }, s);
+}
+template <typename T>
+int axpbyz_many_launch(long N, int Nfields, long offset, T a, const T* x, T b, const T* y, T* z, cudaStream_t s)
+{
+  return ew_many_launch(
+      N, Nfields,
+      [=] __device__(long i, int fld) { z[i + fld * offset] = a * x[i + fld * offset] + b * y[i + fld * offset]; }, s);
+}
+template <typename T>
+int abs_launch(long N, T* x, cudaStream_t s)
+{
+  return ew_launch(N, [=] __device__(long i) { x[i] = x[i] < T(0) ? -x[i] : x[i]; }, s);
+}
+
 template <typename T>
 int add_scalar_launch(long N, DevScalar a, T* x, cudaStream_t s)
 {
@@ -176,7 +230,14 @@ int multi_scaled_add_w_offset_launch(long N, int m, long destOffset, long fieldO
   template int axpbyz_launch<T>(long, DevScalar, const T*, DevScalar, const T*, T*, cudaStream_t);    \
   template int axmyz_launch<T>(long, T, const T*, const T*, T*, cudaStream_t);                        \
   template int scale_launch<T>(long, T, T*, cudaStream_t);                                            \
-  template int add_scalar_launch<T>(long, DevScalar, T*, cudaStream_t);
+  template int add_scalar_launch<T>(long, DevScalar, T*, cudaStream_t);                               \
+  template int scale_many_launch<T>(long, int, long, T, T*, cudaStream_t);                            \
+  template int axmy_many_launch<T>(long, int, long, int, T, const T*, T*, cudaStream_t);              \
+  template int axmyz_many_launch<T>(long, int, long, T, const T*, const T*, T*, cudaStream_t);        \
+  template int ady_many_launch<T>(long, int, long, T, T*, cudaStream_t);                              \
+  template int axdy_launch<T>(long, T, const T*, T*, cudaStream_t);                                   \
+  template int axpbyz_many_launch<T>(long, int, long, T, const T*, T, const T*, T*, cudaStream_t);    \
+  template int abs_launch<T>(long, T*, cudaStream_t);
 NRSB_INST(double)
 NRSB_INST(float)
 #undef NRSB_INST

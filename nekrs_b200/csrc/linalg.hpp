@@ -73,6 +73,21 @@ template <typename T>
 int scale_launch(long N, T a, T* x, cudaStream_t s);
 template <typename T>
 int add_scalar_launch(long N, DevScalar a, T* x, cudaStream_t s);  // x += a
+// "Many" family (linAlg.hpp:75-139): Nfields vectors of N entries, `offset` apart, one launch
+template <typename T>
+int scale_many_launch(long N, int Nfields, long offset, T a, T* x, cudaStream_t s);
+template <typename T>
+int axmy_many_launch(long N, int Nfields, long offset, int mode, T a, const T* x, T* y, cudaStream_t s);
+template <typename T>
+int axmyz_many_launch(long N, int Nfields, long offset, T a, const T* x, const T* y, T* z, cudaStream_t s);
+template <typename T>
+int ady_many_launch(long N, int Nfields, long offset, T a, T* y, cudaStream_t s);  // y = a / y
+template <typename T>
+int axdy_launch(long N, T a, const T* x, T* y, cudaStream_t s);  // y = a x / y
+template <typename T>
+int axpbyz_many_launch(long N, int Nfields, long offset, T a, const T* x, T b, const T* y, T* z, cudaStream_t s);
+template <typename T>
+int abs_launch(long N, T* x, cudaStream_t s);
 int set_scalar_launch(double* dst, DevScalar v, cudaStream_t s);  // dst[0] = v
 int copy_d2f_launch(long N, const double* x, float* y, cudaStream_t s);
 int copy_f2d_launch(long N, const float* x, double* y, cudaStream_t s);

@@ -822,7 +822,36 @@ int MGSolver_t::Run(float* o_rhs, float* o_x)
 {
   levels[0]->o_x = o_x;
   levels[0]->o_rhs = o_rhs;
-  return runVcycle(0);
+  return additive ? runAdditiveVcycle() : runVcycle(0);
+}
+
+// MGSolver.cpp:195-251 (with coarsenV, schwarzSolve, prolongateV of :32-78).  The reference overlaps the CPU
+// (hypre) coarse solve with the device smoothing in a second OpenMP task; here everything is on the device and
+// the coarse solve simply follows on the stream.
+int MGSolver_t::runAdditiveVcycle()
+{
+  const int numLevels = (int)levels.size();
+  int rc;
+  cudaStream_t st = levels[0]->elliptic->stream;
+  // coarsenV: rhs of every level = restriction of the level above
+  for (int k = 0; k < numLevels - 1; ++k) {
+    pMGLevel *level = levels[k].get(), *levelC = levels[k + 1].get();
+    NRSB_CUDA(cudaMemcpyAsync(level->o_res.p, level->o_rhs, sizeof(float) * level->Nrows, cudaMemcpyDeviceToDevice, st));
+    if ((rc = levelC->coarsen(level->o_res.p, levelC->o_rhs))) return rc;
+  }
+  // schwarzSolve: x_k = S_k rhs_k on every level but the coarsest (the reference repeats the restriction here)
+  for (int k = 0; k < numLevels - 1; ++k) {
+    pMGLevel *level = levels[k].get(), *levelC = levels[k + 1].get();
+    if ((rc = level->smooth(level->o_rhs, level->o_x, true))) return rc;
+    NRSB_CUDA(cudaMemcpyAsync(level->o_res.p, level->o_rhs, sizeof(float) * level->Nrows, cudaMemcpyDeviceToDevice, st));
+    if ((rc = levelC->coarsen(level->o_res.p, levelC->o_rhs))) return rc;
+  }
+  pMGLevel* base = levels[baseLevel].get();
+  if ((rc = coarseSolve(base->o_rhs, base->o_x))) return rc;
+  // prolongateV: x_k += P x_{k+1}
+  for (int k = numLevels - 2; k >= 0; --k)
+    if ((rc = levels[k + 1]->prolongate(levels[k + 1]->o_x, levels[k]->o_x))) return rc;
+  return NRSB_OK;
 }
 
 int MGSolver_t::runVcycle(int k)
@@ -958,6 +987,25 @@ int ellipticMultiGridSetup(elliptic_t* elliptic_, precon_t* precon)
   }
   precon->MGSolver.reset(new MGSolver_t());
   MGSolver_t* mg = precon->MGSolver.get();
+  // cycle type and its legality (MGSolver.cpp:99-139)
+  {
+    const bool cheb = options.compareArgs("MULTIGRID SMOOTHER", "CHEBYSHEV");
+    const bool schwarzSm =
+        options.compareArgs("MULTIGRID SMOOTHER", "ASM") || options.compareArgs("MULTIGRID SMOOTHER", "RAS");
+    if (options.has("MGSOLVER CYCLE") && !options.compareArgs("MGSOLVER CYCLE", "VCYCLE")) {
+      set_last_error("Unknown multigrid cycle type!");
+      return NRSB_ERR_INVALID;
+    }
+    mg->additive = options.compareArgs("MGSOLVER CYCLE", "ADDITIVE");
+    if (mg->additive && cheb) {
+      set_last_error("Additive vcycle is not supported for Chebyshev!");
+      return NRSB_ERR_INVALID;
+    }
+    if (!mg->additive && schwarzSm && !cheb) {
+      set_last_error("Multiplicative vcycle is not supported for RAS/ASM smoother without Chebyshev!");
+      return NRSB_ERR_INVALID;
+    }
+  }
   const bool coarseSolveOpt = options.compareArgs("MULTIGRID COARSE SOLVE", "TRUE");
   const bool coarseAndSmooth = options.compareArgs("MULTIGRID COARSE SOLVE AND SMOOTH", "TRUE");
   int rc;
@@ -992,6 +1040,12 @@ int ellipticMultiGridSetup(elliptic_t* elliptic_, precon_t* precon)
         for (int j = 0; j < Nf + 1; ++j) lvl->R[(size_t)i * (Nf + 1) + j] = (float)P[(size_t)j * (Nc + 1) + i];
       lvl->NqF = Nf + 1;
       lvl->NpF = (dlong)(Nf + 1) * (Nf + 1) * (Nf + 1);
+      // nodal interpolation fine -> coarse for the coefficient fields (ellipticBuildMultigridLevel.cpp:133-146)
+      {
+        std::vector<double> I;
+        mesh_t::interp_matrix(zf, zc, I);  // [Nqc][Nqf]
+        e->interpFromFine.assign(I.begin(), I.end());
+      }
       lvl->o_invDegreeFine = fine->o_invDegreePfloat;
       if ((rc = lvl->x_store.alloc(lvl->Nrows))) return rc;
       if ((rc = lvl->rhs_store.alloc(lvl->Nrows))) return rc;

@@ -136,6 +136,22 @@ class Elliptic:
         call("nrsb_elliptic_set_option", self._h, key.encode(), str(value).encode())
         self.options[key.upper()] = str(value).upper()
 
+    def set_coeff_field(self, d_lambda0, d_lambda1=None):
+        """ELLIPTIC COEFF FIELD: per-node coefficients (device fp64 buffers owned by the caller)."""
+        self._keep += [d_lambda0, d_lambda1]
+        call("nrsb_elliptic_set_coeff_field", self._h, vp(d_lambda0), vp(d_lambda1))
+
+    def set_coefficients(self, lambda0, lambda1):
+        call("nrsb_elliptic_set_coefficients", self._h, C.c_double(lambda0), C.c_double(lambda1))
+
+    def update_jacobi(self):
+        """ellipticUpdateJacobi(elliptic)."""
+        call("nrsb_elliptic_update_jacobi", self._h)
+
+    def update_lambda(self):
+        """ellipticMultiGridUpdateLambda(elliptic)."""
+        call("nrsb_elliptic_update_lambda", self._h)
+
     def set_ax_variant(self, precision, variant):
         call("nrsb_elliptic_set_ax_variant", self._h, C.c_int(precision), C.c_int(variant))
 

@@ -198,3 +198,28 @@ class Ogs:
             self.destroy()
         except Exception:
             pass
+
+
+def ellipticBlockBuildDiagonalHex3D(N, Nelements, ggeo, D_host, lambda0, lambda1, Aq, *, Nfields=1, offset=0,
+                                    loffset=0, poisson=True, lambda_field=False, dtype=np.float64, stream=None):
+    prec = 8 if np.dtype(dtype) == np.float64 else 4
+    D_host = np.ascontiguousarray(D_host, dtype=dtype)
+    call("nrsb_ellipticBlockBuildDiagonalHex3D", C.c_int(N + 1), C.c_int(prec), i32(Nelements), C.c_int(Nfields),
+         i32(offset), i32(loffset), vp(ggeo), vp(D_host), vp(lambda0), vp(lambda1), C.c_int(1 if poisson else 0),
+         C.c_int(1 if lambda_field else 0), vp(Aq), vp(stream))
+
+
+def linalg_many(name, prec, *args, stream=None):
+    """nrsb_scaleMany / nrsb_axmyMany / nrsb_axmyzMany / nrsb_adyMany / nrsb_axpbyzMany / nrsb_add / nrsb_axmy /
+    nrsb_axdy / nrsb_abs with ctypes-converted arguments (ints -> int32, floats -> double, buffers -> void*)."""
+    conv = [C.c_int(prec)]
+    for a in args:
+        if isinstance(a, (int, np.integer)):
+            conv.append(i32(int(a)))
+        elif isinstance(a, float):
+            conv.append(C.c_double(a))
+        else:
+            conv.append(vp(a))
+    conv.append(vp(stream))
+    call("nrsb_" + name, *conv)
+

@@ -656,6 +656,22 @@ class OSolver:
         lc.prolongate(lc.x, lv.x, lv.degree)
         lv.smooth(lv.rhs, lv.x, False)
 
+    # ---- additive cycle (MGSolver.cpp:195-251 with coarsenV / schwarzSolve / prolongateV, :32-78): restrict the
+    #      right-hand side to every level, smooth every level from zero, solve the coarse problem, add the prolongated
+    #      corrections.  (The reference runs the coarse solve in a second OpenMP task: same arithmetic.)
+    def additive_vcycle(self):
+        L = self.levels
+        for k in range(len(L) - 1):  # coarsenV
+            L[k].res[:] = L[k].rhs
+            L[k + 1].coarsen(L[k].res, L[k + 1].rhs, L[k].ell.inv_degree_f, L[k].degree)
+        for k in range(len(L) - 1):  # schwarzSolve
+            L[k].smooth(L[k].rhs, L[k].x, True)
+            L[k].res[:] = L[k].rhs
+            L[k + 1].coarsen(L[k].res, L[k + 1].rhs, L[k].ell.inv_degree_f, L[k].degree)
+        self.coarse_solve(L[-1].rhs, L[-1].x)
+        for k in range(len(L) - 2, -1, -1):  # prolongateV
+            L[k + 1].prolongate(L[k + 1].x, L[k].x, L[k].degree)
+
     def coarse_solve(self, rhs, x):
         base = self.levels[-1]
         if self.coarse is None:
@@ -678,7 +694,10 @@ class OSolver:
             l0 = self.levels[0]
             l0.x[:] = 0
             orc.copy_d2f(np.ascontiguousarray(r[:n]), l0.rhs)
-            self.vcycle(0)
+            if compare(o, "MGSOLVER CYCLE", "ADDITIVE"):
+                self.additive_vcycle()
+            else:
+                self.vcycle(0)
             zz = np.zeros(n)
             orc.copy_f2d(l0.x, zz)
             z[:n] = zz

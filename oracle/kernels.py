@@ -267,3 +267,40 @@ class RefLinAlg:
 
     def copy_f2d(self, x, y):
         self.lib.copyPfloatToDfloat(_r(x.size), _p(x), _p(y))
+
+
+def build_diagonal(N, E, ggeo, D, lambda0, lambda1, poisson=True, lambda_field=False, Nfields=1, offset=None,
+                   loffset=0):
+    """ellipticBlockBuildDiagonalHex3D.okl:26-118 (OKL only): Aq[id + l*offset] = element diagonal of
+    D^T (lambda0 G) D (+ lambda1 GwJ).  numpy restatement of the thread body; the accumulation runs in the dtype of
+    ggeo like the kernel's dfloat / pfloat."""
+    Nq = N + 1
+    Np = Nq ** 3
+    dt = ggeo.dtype
+    G = ggeo.reshape(E, 7, Nq, Nq, Nq)
+    Dd = np.asarray(D, dtype=dt)
+    D2 = Dd * Dd
+    dd = np.diag(Dd).astype(dt)
+    offset = E * Np if offset is None else offset
+    out = np.zeros(max(Nfields * offset, E * Np), dtype=dt)
+    for l in range(Nfields):
+        if lambda_field:
+            l0 = lambda0[l * loffset:l * loffset + E * Np].reshape(E, Nq, Nq, Nq).astype(dt)
+        else:
+            l0 = np.full((E, Nq, Nq, Nq), lambda0[0], dtype=dt)
+        r = np.zeros((E, Nq, Nq, Nq), dtype=dt)
+        r += dt.type(2) * G[:, 1] * l0 * dd[None, None, None, :] * dd[None, None, :, None]
+        r += dt.type(2) * G[:, 4] * l0 * dd[None, None, None, :] * dd[None, :, None, None]
+        r += dt.type(2) * G[:, 3] * l0 * dd[None, None, :, None] * dd[None, :, None, None]
+        r += np.einsum("ekjm,mi->ekji", G[:, 0] * l0, D2).astype(dt)
+        r += np.einsum("ekmi,mj->ekji", G[:, 2] * l0, D2).astype(dt)
+        r += np.einsum("emji,mk->ekji", G[:, 5] * l0, D2).astype(dt)
+        if not poisson:
+            if lambda_field:
+                l1 = lambda1[l * loffset:l * loffset + E * Np].reshape(E, Nq, Nq, Nq).astype(dt)
+            else:
+                l1 = dt.type(lambda1[0])
+            r += G[:, 6] * l1
+        out[l * offset:l * offset + E * Np] = r.reshape(-1)
+    return out
+

@@ -263,6 +263,153 @@ def test_preconditioner_vcycle_output(orc):
     assert abs(ell.get_int("coarseIterations") - ref.coarse.last_iter) <= 8
 
 
+@pytest.mark.parametrize("smoother", ["RAS", "ASM"])
+def test_additive_vcycle(orc, smoother):
+    """MGSOLVER CYCLE = VCYCLE+ADDITIVE (MGSolver.cpp:195-251; ethier CI mode 14, examples/ethier/ci.inc:802-815):
+    one preconditioner application against the oracle's restatement, then a whole FGMRES solve (iterations +-1).
+    Chebyshev + additive, and Schwarz without Chebyshev in the multiplicative cycle, are rejected as the
+    reference does (MGSolver.cpp:102-133)."""
+    extra = {"MGSOLVER CYCLE": "VCYCLE+ADDITIVE"}
+    mesh, opts, ell, ref = _mg_case(orc, 7, (3, 2, 2), smoother, extra, eps=1.0)  # undeformed box: 13-15 iterations
+    n = mesh.Nelements * mesh.Np
+    r = np.random.Generator(np.random.PCG64(9)).random(n)
+    r[ref.ell.mask_ids] = 0
+    ref.orc.gs_add(ref.ell.ogs, r)
+    z_ref = np.zeros(n)
+    ref.preconditioner(r, z_ref)
+    d_z = DB.zeros(ell.fieldOffset, np.float64)
+    ell.preconditioner(DB(like=padded(r, ell.fieldOffset)), d_z)
+    assert relerr(d_z.download()[:n], z_ref) < 2e-4
+    rhs = meshgen.kershaw_rhs(mesh)
+    x_ref = ref.solve(rhs, np.zeros(n))
+    x = np.zeros(n)
+    it = ell.solve_host(rhs, x)
+    assert abs(it - ref.Niter) <= 1, (it, ref.Niter)
+    assert relerr(x, x_ref) < 1e-6
+    with pytest.raises(lib.NrsbError, match="Additive vcycle is not supported for Chebyshev"):
+        Elliptic(mesh, dict(opts, **{"MULTIGRID SMOOTHER": "FOURTHOPTCHEBYSHEV+" + smoother}))
+    with pytest.raises(lib.NrsbError, match="Multiplicative vcycle is not supported"):
+        Elliptic(mesh, dict(opts, **{"MGSOLVER CYCLE": "VCYCLE"}))
+
+
+def _ax_field(orc, ref, N, q, lam0, lam1, poisson):
+    """oracle Ax with per-node coefficients (p_lambda = 1 in ellipticPartialAxCoeffHex3D.c)."""
+    import ctypes as C
+    m = ref.mesh
+    E = m.E
+    el = np.arange(E, dtype=np.int32)
+    S = np.ascontiguousarray(m.D.T)
+    out = np.zeros(E * m.Np)
+    l1 = lam1 if lam1 is not None else np.zeros(1)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    orc.lib.orc_ax_d(C.c_int(E), C.c_int(0), C.c_int(0), p(el), p(m.ggeo), p(m.D), p(S), p(lam0), p(l1), p(q), p(out),
+                     C.c_int(N + 1), C.c_int(1 if poisson else 0), C.c_int(1))
+    return out
+
+
+def test_coefficient_field_jacobi_handle(orc):
+    """ELLIPTIC COEFF FIELD through the handle: variable lambda0 / lambda1 in the operator (ellipticOperator.cpp:83-93
+    with p_lambda), device ellipticUpdateJacobi (diagonal kernel + gather-scatter + adyMany), a Jacobi-PCG solve of a
+    manufactured solution, then back to constants through nrsb_elliptic_set_coefficients."""
+    from oracle import kernels as K
+    N = 7
+    mesh = meshgen.box_mesh(N, (3, 2, 2), kershaw_eps=0.4)
+    opts = {"SOLVER": "PCG", "PRECONDITIONER": "JACOBI", "MAXIMUM ITERATIONS": "500", "SOLVER TOLERANCE": "1e-10",
+            "LINEAR SOLVER STOPPING CRITERION": "RELATIVE"}
+    ell = Elliptic(mesh, opts, poisson=False, lambda0=1.0, lambda1=0.5, name="scalar")
+    ref = driver.OSolver(mesh, {"SOLVER": "PCG", "PRECONDITIONER": "NONE"}, orc)
+    n = mesh.Nelements * mesh.Np
+    x, y, z = mesh.x.ravel(), mesh.y.ravel(), mesh.z.ravel()
+    lam0 = 1.0 + 0.5 * np.sin(2 * x) * np.cos(y) + 0.2 * z
+    lam1 = 0.3 + 0.2 * np.cos(3 * x * y)
+    d_l0, d_l1 = DB(like=padded(lam0, ell.fieldOffset)), DB(like=padded(lam1, ell.fieldOffset))
+    ell.set_coeff_field(d_l0, d_l1)
+    q = np.random.Generator(np.random.PCG64(31)).random(n)
+    out_ref = _ax_field(orc, ref, N, q, lam0, lam1, False)
+    ref.ell.apply_mask(out_ref)
+    orc.gs_add(ref.ell.ogs, out_ref)
+    d_q, d_Aq = DB(like=padded(q, ell.fieldOffset)), DB.zeros(ell.fieldOffset, np.float64)
+    ell.operator(d_q, d_Aq)
+    assert relerr(d_Aq.download()[:n], out_ref) < 1e-12
+    # inverse diagonal
+    diag = K.build_diagonal(N, mesh.Nelements, ref.mesh.ggeo.reshape(mesh.Nelements, 7, mesh.Np), ref.mesh.D, lam0,
+                            lam1, poisson=False, lambda_field=True)
+    orc.gs_add(ref.ell.ogs, diag)
+    assert relerr(ell.get_array("invDiagA", np.float64), 1.0 / diag) < 1e-12
+    # manufactured solution
+    x_true = np.sin(np.pi * x) * np.sin(np.pi * y) * np.sin(np.pi * z)
+    x_true[ref.ell.mask_ids] = 0.0
+    d_b = DB.zeros(ell.fieldOffset, np.float64)
+    ell.ax(DB(like=padded(x_true, ell.fieldOffset)), d_b)
+    d_x = DB.zeros(ell.fieldOffset, np.float64)
+    it = ell.solve(d_b, d_x)
+    assert 0 < it < 500
+    assert relerr(d_x.download()[:n], x_true) < 1e-7
+    # back to constants, changed
+    ell.set_coeff_field(None, None)
+    ell.set_coefficients(2.0, 0.25)
+    el = np.arange(mesh.Nelements, dtype=np.int32)
+    out_c = np.zeros(n)
+    orc.ax(N, el, ref.mesh.ggeo, ref.mesh.D, q, out_c, np.array([2.0]), np.array([0.25]), poisson=False)
+    ref.ell.apply_mask(out_c)
+    orc.gs_add(ref.ell.ogs, out_c)
+    ell.operator(d_q, d_Aq)
+    assert relerr(d_Aq.download()[:n], out_c) < 1e-12
+    diag = K.build_diagonal(N, mesh.Nelements, ref.mesh.ggeo.reshape(mesh.Nelements, 7, mesh.Np), ref.mesh.D,
+                            np.array([2.0]), np.array([0.25]), poisson=False)
+    orc.gs_add(ref.ell.ogs, diag)
+    assert relerr(ell.get_array("invDiagA", np.float64), 1.0 / diag) < 1e-12
+
+
+def test_coefficient_field_multigrid_levels(orc):
+    """ellipticMultiGridUpdateLambda: level 0 holds the fp32 cast of the coefficient field, coarser levels its nodal
+    interpolation; ellipticUpdateJacobi refreshes the DAMPEDJACOBI smoother diagonals of the levels from them; the
+    variable-coefficient Poisson solve then converges to a manufactured solution."""
+    from oracle import kernels as K
+    from oracle import sem
+    N = 7
+    mesh = meshgen.box_mesh(N, (2, 2, 2), kershaw_eps=0.6)
+    opts = pressure_options(**{"MULTIGRID SMOOTHER": "CHEBYSHEV+DAMPEDJACOBI", "SOLVER": "PCG+FLEXIBLE",
+                               "ELLIPTIC PRECO COEFF FIELD": "TRUE", "MAXIMUM ITERATIONS": "300"})
+    ell = Elliptic(mesh, opts)
+    ref = driver.OSolver(mesh, opts, orc)
+    n = mesh.Nelements * mesh.Np
+    x, y, z = mesh.x.ravel(), mesh.y.ravel(), mesh.z.ravel()
+    lam0 = 1.0 + 0.4 * np.sin(2 * x + y) + 0.3 * z * z
+    d_l0 = DB(like=padded(lam0, ell.fieldOffset))
+    ell.set_coeff_field(d_l0, None)
+    orders = [L.degree for L in ref.levels]
+    prev = lam0.astype(np.float32)
+    for k, Nc in enumerate(orders):
+        if k > 0:
+            prev = sem.interpolate_nodes(prev.astype(np.float64), orders[k - 1], Nc).astype(np.float32)
+        got = ell.get_array("level%d:lambda0Field" % k, np.float32)
+        assert relerr(got, prev) < 2e-6, k
+        L = ref.levels[k]
+        if k == len(orders) - 1:
+            continue  # coarse solve instead of a smoother
+        g = L.ell.mesh.ggeo_f.reshape(mesh.Nelements, 7, (Nc + 1) ** 3)
+        diag = K.build_diagonal(Nc, mesh.Nelements, g, L.ell.mesh.D_f, got, np.zeros(1, np.float32), poisson=True,
+                                lambda_field=True)
+        orc.gs_add(L.ell.ogs, diag)
+        assert relerr(ell.get_array("level%d:invDiagA" % k, np.float32), (np.float32(1) / diag)) < 5e-5, k
+    q = np.random.Generator(np.random.PCG64(33)).random(n)
+    out_ref = _ax_field(orc, ref, N, q, lam0, None, True)
+    ref.ell.apply_mask(out_ref)
+    orc.gs_add(ref.ell.ogs, out_ref)
+    d_q, d_Aq = DB(like=padded(q, ell.fieldOffset)), DB.zeros(ell.fieldOffset, np.float64)
+    ell.operator(d_q, d_Aq)
+    assert relerr(d_Aq.download()[:n], out_ref) < 1e-12
+    x_true = np.sin(np.pi * x) * np.sin(np.pi * y) * np.sin(np.pi * z)
+    x_true[ref.ell.mask_ids] = 0.0
+    d_b = DB.zeros(ell.fieldOffset, np.float64)
+    ell.ax(DB(like=padded(x_true, ell.fieldOffset)), d_b)
+    d_x = DB.zeros(ell.fieldOffset, np.float64)
+    it = ell.solve(d_b, d_x)
+    assert 0 < it < 60, it
+    assert relerr(d_x.download()[:n], x_true) < 1e-6
+
+
 def test_solution_projection(orc):
     mesh = meshgen.box_mesh(5, (2, 2, 2), kershaw_eps=0.4)
     opts = {"SOLVER": "PCG", "PRECONDITIONER": "JACOBI", "MAXIMUM ITERATIONS": "300", "SOLVER TOLERANCE": "1e-9",

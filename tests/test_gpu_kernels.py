@@ -349,3 +349,79 @@ def test_geometric_factors(orc, N):
     assert relerr(d_g.download(), ref.ravel()) < 1e-12
     assert relerr(d_J.download(), Jref.ravel()) < 1e-12
     assert np.all(d_J.download() > 0)   # meshGeometricFactorsHex3D.cpp:52-58
+
+
+# ------------------------------------------------------------------------------------ diagonal, linAlg "Many"
+@pytest.mark.parametrize("N", [1, 3, 7, 9])
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("poisson,field,Nfields", [(True, False, 1), (False, False, 1), (False, True, 1), (True, True, 3),
+                                                   (False, True, 3)])
+def test_build_diagonal(N, dt, poisson, field, Nfields):
+    from oracle import kernels as K
+    E, Np = 23, (N + 1) ** 3
+    r = rng(50 + N)
+    g, _ = sem.jacobi_gll(N)
+    D = sem.dmatrix_1d(g).astype(dt)
+    ggeo = (r.random((E, 7, Np)) + 0.1).astype(dt)
+    offset = E * Np + 40
+    loffset = E * Np + 8
+    if field:
+        lam0 = (r.random(Nfields * loffset) + 0.5).astype(dt)
+        lam1 = r.random(Nfields * loffset).astype(dt)
+    else:
+        lam0, lam1 = np.array([1.3], dtype=dt), np.array([0.7], dtype=dt)
+    ref = K.build_diagonal(N, E, ggeo, D, lam0, lam1, poisson=poisson, lambda_field=field, Nfields=Nfields,
+                           offset=offset, loffset=loffset)
+    d_Aq = DB.zeros(Nfields * offset, dt)
+    ops.ellipticBlockBuildDiagonalHex3D(N, E, DB(like=ggeo), D, DB(like=lam0), DB(like=lam1), d_Aq, Nfields=Nfields,
+                                        offset=offset, loffset=loffset, poisson=poisson, lambda_field=field, dtype=dt)
+    out = d_Aq.download(dt)
+    for l in range(Nfields):
+        sl = slice(l * offset, l * offset + E * Np)
+        assert relerr(out[sl], ref[sl]) < (1e-12 if dt == np.float64 else 2e-5)
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_linalg_many_family(dt):
+    """scaleMany, add, abs, axmy(Many), axmyzMany, adyMany, axdy, axpbyzMany (linAlg.hpp:70-142) against numpy."""
+    prec = 8 if dt == np.float64 else 4
+    N, Nf, off = 1000, 3, 1031
+    r = rng(77)
+    x = (r.random(Nf * off) + 0.5).astype(dt)
+    y = (r.random(Nf * off) - 0.5).astype(dt)
+    tol = 1e-14 if dt == np.float64 else 1e-6
+
+    def fields(a):
+        return np.concatenate([a[f * off:f * off + N] for f in range(Nf)])
+
+    d = DB(like=x)
+    ops.linalg_many("scaleMany", prec, N, Nf, off, 1.7, d)
+    assert relerr(fields(d.download(dt)), fields(x) * dt(1.7)) < tol
+    untouched = d.download(dt)[N:off]
+    assert np.array_equal(untouched, x[N:off])          # the gap between fields is not written
+    d = DB(like=y)
+    ops.linalg_many("add", prec, N, 0.25, d)
+    assert relerr(d.download(dt)[:N], y[:N] + dt(0.25)) < tol
+    d = DB(like=y)
+    ops.linalg_many("abs", prec, N, d)
+    assert np.array_equal(d.download(dt)[:N], np.abs(y[:N]))
+    d = DB(like=y)
+    ops.linalg_many("axmy", prec, N, 2.0, DB(like=x), d)
+    assert relerr(d.download(dt)[:N], dt(2) * x[:N] * y[:N]) < tol
+    for mode in (0, 1):
+        d = DB(like=y)
+        ops.linalg_many("axmyMany", prec, N, Nf, off, mode, 0.5, DB(like=x), d)
+        xx = fields(x) if mode else np.tile(x[:N], Nf)
+        assert relerr(fields(d.download(dt)), dt(0.5) * xx * fields(y)) < tol
+    d = DB.zeros(Nf * off, dt)
+    ops.linalg_many("axmyzMany", prec, N, Nf, off, 3.0, DB(like=x), DB(like=y), d)
+    assert relerr(fields(d.download(dt)), dt(3) * fields(x) * fields(y)) < tol
+    d = DB(like=x)
+    ops.linalg_many("adyMany", prec, N, Nf, off, 1.0, d)
+    assert relerr(fields(d.download(dt)), dt(1) / fields(x)) < tol
+    d = DB(like=x)
+    ops.linalg_many("axdy", prec, N, 2.0, DB(like=y), d)
+    assert relerr(d.download(dt)[:N], dt(2) * y[:N] / x[:N]) < tol
+    d = DB.zeros(Nf * off, dt)
+    ops.linalg_many("axpbyzMany", prec, N, Nf, off, 2.0, DB(like=x), -3.0, DB(like=y), d)
+    assert relerr(fields(d.download(dt)), dt(2) * fields(x) + dt(-3) * fields(y)) < tol

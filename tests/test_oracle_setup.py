@@ -163,3 +163,30 @@ def test_helmholtz_branch_of_the_driver(orc):
     assert 0 < s.Niter < 400
     assert np.max(np.abs(x - x_true)) / np.max(np.abs(x_true)) < 1e-7
     assert s.ell.allNeumann == 0
+
+
+def test_diagonal_restatement_equals_unit_vector_probes_of_the_oracle_ax(orc):
+    """oracle/kernels.build_diagonal (restated from ellipticBlockBuildDiagonalHex3D.okl, which has no serial .c) must
+    equal diag(A_e) obtained by applying the pinned oracle Ax (variable coefficients, Helmholtz) to unit vectors."""
+    import ctypes as C
+    from oracle import kernels as K
+    N, E = 2, 2
+    Np = (N + 1) ** 3
+    r = np.random.default_rng(1)
+    g, _ = sem.jacobi_gll(N)
+    D = sem.dmatrix_1d(g)
+    ggeo = r.random((E, 7, Np)) + 0.1
+    lam0, lam1 = r.random(E * Np) + 0.5, r.random(E * Np)
+    el = np.arange(E, dtype=np.int32)
+    S = np.ascontiguousarray(D.T)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    diag = np.zeros(E * Np)
+    for n in range(E * Np):
+        q = np.zeros(E * Np)
+        q[n] = 1
+        out = np.zeros(E * Np)
+        orc.lib.orc_ax_d(C.c_int(E), C.c_int(0), C.c_int(0), p(el), p(ggeo), p(D), p(S), p(lam0), p(lam1), p(q), p(out),
+                         C.c_int(N + 1), C.c_int(0), C.c_int(1))
+        diag[n] = out[n]
+    ref = K.build_diagonal(N, E, ggeo, D, lam0, lam1, poisson=False, lambda_field=True)
+    assert np.max(np.abs(ref - diag)) / np.max(np.abs(diag)) < 1e-14
