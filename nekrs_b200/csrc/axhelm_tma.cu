@@ -301,7 +301,12 @@ __global__ void __launch_bounds__(NGROUPS* Nq* Nq + 32, 1)
     }
     __syncthreads();
     if (stamp) F.stamps[1] = globaltimer_ns();
-    halo_pack_store<T, 16, true>(H, gs_op::add, Aq, (T*)F.partial, e00, estride, first);
+    {
+      T val[16];
+      halo_pack_gather<T, 16, true>(H, gs_op::add, Aq, e00, estride, first, val);
+      if (stamp) F.stamps[5] = globaltimer_ns() + (val[0] == T(12345.678) ? 1 : 0);  // (after the values arrived)
+      halo_pack_scatter<T, 16>(H, (T*)F.partial, e00, estride, first, val);
+    }
     for (int e0 = e00 + 16 * estride; e0 < H.nSend; e0 += 8 * estride)
       halo_pack_flat<T, 8, true>(H, gs_op::add, Aq, (T*)F.partial, e0, estride);
     if (stamp) F.stamps[2] = globaltimer_ns();

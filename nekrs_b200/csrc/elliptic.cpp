@@ -40,6 +40,10 @@ int elliptic_t::read_scalars(int first, int count, double* out)
   NRSB_CUDA(cudaMemcpyAsync(h_scal + first, o_scal.p + first, sizeof(double) * count, cudaMemcpyDeviceToHost, stream));
   NRSB_CUDA(cudaStreamSynchronize(stream));
   for (int i = 0; i < count; ++i) out[i] = h_scal[first + i];
+  if (comm && comm->peer_timeout()) {
+    set_last_error("a device-side wait for a peer rank timed out (halo flags / all-reduce): a rank is missing");
+    return NRSB_ERR_CUDA;
+  }
   return NRSB_OK;
 }
 
@@ -270,9 +274,9 @@ int ellipticOperator(elliptic_t* elliptic, const T* o_q, T* o_Aq, bool masked, A
         unsigned long long h[16];
         cudaMemcpy(h, F.stamps, sizeof(h), cudaMemcpyDeviceToHost);
         fprintf(stderr,
-                "[rank %d]   last launch, ns after pusher start: halo elements stored %lld, pushed %lld, fenced %lld, "
+                "[rank %d]   last launch, ns after pusher start: halo elements stored %lld, values loaded %lld, pushed %lld, fenced %lld, "
                 "flags %lld, axhelm CTA 0 done %lld, last axhelm CTA done %lld\n",
-                mesh->comm ? mesh->comm->rank : 0, (long long)(h[1] - h[0]), (long long)(h[2] - h[0]),
+                mesh->comm ? mesh->comm->rank : 0, (long long)(h[1] - h[0]), (long long)(h[5] - h[0]), (long long)(h[2] - h[0]),
                 (long long)(h[3] - h[0]), (long long)(h[4] - h[0]), (long long)(h[8] - h[0]), (long long)(h[9] - h[0]));
         nrec = 0;
       }

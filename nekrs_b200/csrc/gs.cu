@@ -20,6 +20,7 @@
 
 #include "common.cuh"
 #include "gs.hpp"
+#include "halo.cuh"
 
 namespace nrsb {
 
@@ -39,12 +40,8 @@ constexpr int kGsBS = 128;
 constexpr int kGsMaskPerThread = 4;
 
 template <typename T, int kRP>
-__global__ void __launch_bounds__(kGsBS, 2048 / kGsBS)
-    gs_rows_kernel(const GsRowsDev R, const GsGrid G, const dlong stride, T* __restrict__ q)
+__device__ __forceinline__ void gs_rows_body(const GsRowsDev& R, const GsGrid& G, int b, T* __restrict__ qf)
 {
-  pdl_trigger();  // a persistent axhelm launch behind this kernel may start its prologue on drained SMs
-  T* __restrict__ qf = q + (size_t)blockIdx.y * stride;
-  int b = blockIdx.x;
   const int t = threadIdx.x;
   if (b < G.pairBlocks) {
     int2 id[kRP];
@@ -150,6 +147,79 @@ __global__ void __launch_bounds__(kGsBS, 2048 / kGsBS)
   }
 }
 
+template <typename T, int kRP>
+__global__ void __launch_bounds__(kGsBS, 2048 / kGsBS)
+    gs_rows_kernel(const GsRowsDev R, const GsGrid G, const dlong stride, T* __restrict__ q)
+{
+  pdl_trigger();  // a persistent axhelm launch behind this kernel may start its prologue on drained SMs
+  gs_rows_body<T, kRP>(R, G, blockIdx.x, q + (size_t)blockIdx.y * stride);
+}
+
+// oogs::finish for one field and ogsAdd (the operator's case): the on-rank rows and the mask exactly as above, plus
+// one more block kind at the END of the grid for the halo rows: table entries first, then the wait for the peers'
+// epoch flags (normally long raised: the peers pushed while this rank was still in axhelm), then
+//   own partial + received partials in ascending rank order -> every local copy
+// (unpackBuf of okl/oogs.okl:121-272 + the scatter).  Rows with more than 3 contributions or more than 2 local
+// copies (element corners on rank edges) take the CSR walk.
+template <typename T, int kRP>
+__global__ void __launch_bounds__(kGsBS, 2048 / kGsBS)
+    gs_rows_halo_kernel(const GsRowsDev R, const GsGrid G, const int localBlocks, const HaloExchangeDev H,
+                        const T* __restrict__ partial, T* __restrict__ v)
+{
+  pdl_trigger();
+  if ((int)blockIdx.x < localBlocks) {
+    gs_rows_body<T, kRP>(R, G, blockIdx.x, v);
+    return;
+  }
+  const int row = (blockIdx.x - localBlocks) * kGsBS + threadIdx.x;
+  int4 rf = make_int4(0, 0, 0, -1), rl = make_int4(-1, -1, 0, 0);
+  if (row < H.nRows) {
+    rf = H.recvFlat[row];
+    rl = H.rowLocal[row];
+  }
+  pdl_wait();
+  for (int i = threadIdx.x; i < H.nPeers * kFlagSlots; i += blockDim.x) {
+    volatile unsigned long long* f = H.myFlags + (size_t)H.peerRank[i / kFlagSlots] * kFlagSlots + i % kFlagSlots;
+    const long long t0 = clock64();
+    while (*f < H.epoch) {
+      if (clock64() - t0 > (1ll << 34)) {  // ~8 s: a peer died; flag it instead of hanging the box
+        if (H.err) *H.err = 1;
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  __threadfence_system();
+  if (row >= H.nRows) return;
+  const volatile T* w = (const volatile T*)H.myWindow;
+  if (rf.w > 0 && rl.z <= 2) {
+    const T own = partial[row];
+    const T a = w[rf.x];
+    const T b = (rf.w == 3) ? w[rf.y] : T(0);
+    T tot;
+    if (rf.w == 2) {
+      tot = (rf.z == 0) ? own + a : a + own;
+    } else {  // three contributions, own partial at position rf.z, the two remote ones in ascending rank order
+      const T c0 = (rf.z == 0) ? own : a;
+      const T c1 = (rf.z == 0) ? a : (rf.z == 1 ? own : b);
+      const T c2 = (rf.z == 2) ? own : b;
+      tot = (c0 + c1) + c2;
+    }
+    v[rl.x] = tot;
+    if (rl.y >= 0) v[rl.y] = tot;
+    return;
+  }
+  T tot = T(0);
+  bool first = true;
+  for (int c = H.recvStarts[row]; c < H.recvStarts[row + 1]; ++c) {
+    const int p = H.recvPeer[c];
+    const T val = (p < 0) ? partial[row] : w[(size_t)H.peerRecvOffset[p] + H.recvSlot[c]];
+    tot = first ? val : tot + val;
+    first = false;
+  }
+  for (int c = H.rowStarts[row]; c < H.rowStarts[row + 1]; ++c) v[H.rowIds[c]] = tot;
+}
+
 template <typename T>
 int gs_rows_launch(const GsRowsDev& R, int Nfields, dlong stride, T* q, cudaStream_t stream)
 {
@@ -176,6 +246,32 @@ int gs_rows_launch(const GsRowsDev& R, int Nfields, dlong stride, T* q, cudaStre
   NRSB_CUDA(launch_pdl_consumer(kern, grid, dim3(kGsBS), 0, stream, R, G, stride, q));
   return NRSB_OK;
 }
+template <typename T>
+int gs_rows_halo_launch(const GsRowsDev& R, const HaloExchangeDev& H, const T* partial, T* v, cudaStream_t stream)
+{
+  auto blocks = [](long n, long per) { return (int)((n + per - 1) / per); };
+  GsGrid G;
+  G.quadBlocks = blocks(R.nQuads, kGsBS);
+  G.octBlocks = blocks(R.nOcts, kGsBS);
+  G.genBlocks = blocks(R.nGen, kGsBS);
+  G.maskBlocks = blocks(R.nMasked, (long)kGsBS * kGsMaskPerThread);
+  const int haloBlocks = blocks(H.nRows, kGsBS);
+  const long wave = (long)kNumSMs * (2048 / kGsBS);
+  const int rpMax = sizeof(T) == 8 ? 3 : 4;
+  int rp = 1;
+  const long others = (long)G.quadBlocks + G.octBlocks + G.genBlocks + G.maskBlocks + haloBlocks;
+  while (rp < rpMax && (long)blocks(R.nPairs, (long)kGsBS * rp) + others > wave) ++rp;
+  G.pairBlocks = blocks(R.nPairs, (long)kGsBS * rp);
+  const int localBlocks = G.pairBlocks + G.quadBlocks + G.octBlocks + G.genBlocks + G.maskBlocks;
+  auto kern = rp == 1 ? gs_rows_halo_kernel<T, 1> : rp == 2 ? gs_rows_halo_kernel<T, 2>
+                      : rp == 3 ? gs_rows_halo_kernel<T, 3> : gs_rows_halo_kernel<T, 4>;
+  NRSB_CUDA(launch_pdl_consumer(kern, dim3(localBlocks + haloBlocks), dim3(kGsBS), 0, stream, R, G, localBlocks, H,
+                                partial, v));
+  return NRSB_OK;
+}
+template int gs_rows_halo_launch<double>(const GsRowsDev&, const HaloExchangeDev&, const double*, double*, cudaStream_t);
+template int gs_rows_halo_launch<float>(const GsRowsDev&, const HaloExchangeDev&, const float*, float*, cudaStream_t);
+
 template int gs_rows_launch<double>(const GsRowsDev&, int, dlong, double*, cudaStream_t);
 template int gs_rows_launch<float>(const GsRowsDev&, int, dlong, float*, cudaStream_t);
 

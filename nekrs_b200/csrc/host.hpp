@@ -77,6 +77,15 @@ class comm_t {
   // generic host collectives used at setup time, provided by the bootstrap layer
   std::function<void(void*, size_t)> allgather_bytes;  // in-place: buffer holds nranks blocks
   std::function<void()> barrier;
+  // device-visible error word (pinned, mapped): a kernel that gave up waiting for a peer (halo flags, all-reduce
+  // slots) sets it instead of hanging; the host turns it into NRSB_ERR_CUDA at its next synchronisation point
+  int* h_err = nullptr;
+  int* d_err = nullptr;
+  ~comm_t()
+  {
+    if (h_err) cudaFreeHost(h_err);
+  }
+  bool peer_timeout() const { return h_err && *h_err != 0; }
 };
 
 int comm_setup_reduce(comm_t* c);

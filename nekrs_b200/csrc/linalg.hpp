@@ -49,6 +49,7 @@ struct PeerReduce {
   double* const* slots = nullptr;              // slots[p] -> peer p's window: [parity][nranks][kMaxRed]
   unsigned long long* const* flags = nullptr;  // flags[p] -> peer p's flags:  [nranks]
   unsigned long long* epoch = nullptr;         // local call counter
+  int* err = nullptr;                          // host-mapped error word (comm_t::d_err)
 };
 
 constexpr int kMaxRed = 16;        // values reduced by one launch

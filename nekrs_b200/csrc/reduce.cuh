@@ -57,7 +57,12 @@ __device__ __forceinline__ void peer_allreduce_warp(const PeerReduce& P, double*
       volatile unsigned long long* f = P.flags[p] + P.rank;
       *f = e;
       volatile unsigned long long* mine = P.flags[P.rank];
+      const long long t0 = clock64();
       while (mine[p] < e) {
+        if (clock64() - t0 > (1ll << 34)) {  // ~8 s: a peer never arrived; flag it instead of hanging the box
+          if (P.err) *P.err = 1;
+          break;
+        }
       }
       __threadfence_system();
       const volatile double* loc = P.slots[P.rank] + ((size_t)par * P.nranks + p) * kMaxRed;
