@@ -285,6 +285,8 @@ int nrsb_elliptic_level_op(nrsb_elliptic_t h, int level, const char* op, float* 
  * "N","Nlocal","Nmasked","lambda1","lambda0","maxEig","downDegree","upDegree" ; "volume" */
 int nrsb_elliptic_get_int(nrsb_elliptic_t h, const char* key, int64_t* value);
 int nrsb_elliptic_get_real(nrsb_elliptic_t h, const char* key, double* value);
+/* "level<k>:maxEig": overwrite that level's lambda_max(S A) estimate (the Chebyshev bounds follow) */
+int nrsb_elliptic_set_real(nrsb_elliptic_t h, const char* key, double value);
 /* arrays (HOST out): "maskIds" (int32), "invDegree" (double), "resHistory" (double, length Niter),
  * "level<k>:invDegree", "level<k>:maskIds", "level<k>:Sx|Sy|Sz|invL|wts" (float) ; returns count */
 int nrsb_elliptic_get_array(nrsb_elliptic_t h, const char* key, void* out_host, int64_t capacity, int64_t* count);

@@ -514,6 +514,30 @@ int nrsb_elliptic_get_real(nrsb_elliptic_t h, const char* key, double* value)
   return NRSB_OK;
 }
 
+/* "level<k>:maxEig": replace the Arnoldi estimate of lambda_max(S A) of that level (ellipticMultiGridLevelSetup.cpp:
+ * 109-180; the reference's estimate starts from a std::random_device vector and is not reproducible) and re-derive
+ * the Chebyshev bounds from it.  Lets a parity test feed the SAME bound to both implementations. */
+int nrsb_elliptic_set_real(nrsb_elliptic_t h, const char* key, double value)
+{
+  NRSB_REQUIRE(h && key, "NULL argument");
+  elliptic_t& e = h->impl;
+  int level;
+  std::string name;
+  if (split_level_key(std::string(key), level, name) && name == "maxEig") {
+    NRSB_REQUIRE(e.precon && e.precon->MGSolver && level >= 0 && level < (int)e.precon->MGSolver->levels.size(),
+                 "no such level");
+    pMGLevel* L = e.precon->MGSolver->levels[level].get();
+    NRSB_REQUIRE(L->maxEig > 0 && value > 0, "level has no Chebyshev smoother");
+    const double f = value / L->maxEig;
+    L->lambda1 *= f;
+    L->lambda0 *= f;
+    L->maxEig = value;
+    return NRSB_OK;
+  }
+  set_last_error(std::string("unknown key ") + key);
+  return NRSB_ERR_INVALID;
+}
+
 int nrsb_elliptic_get_array(nrsb_elliptic_t h, const char* key, void* out_host, int64_t capacity, int64_t* count)
 {
   NRSB_REQUIRE(h && key && count, "NULL argument");

@@ -283,7 +283,11 @@ int ellipticOperator(elliptic_t* elliptic, const T* o_q, T* o_Aq, bool masked, A
     }
     return rc;
   }
-  if (elliptic->overlap) {
+  // The reference's split (Ax on the halo elements, oogs::start, Ax on the interior, oogs::finish: four launches and a
+  // system-scope fence here) only pays when the exchange is slow.  With the one-launch flag-in-data exchange
+  // (oogs_t::exchange_ll) the unsplit form below -- Ax on all elements, then ONE gather-scatter + exchange launch --
+  // is faster on every multigrid level; ENABLE GS COMM OVERLAP = SPLIT keeps the reference's sequence.
+  if (elliptic->overlap && elliptic->options.compareArgs("ENABLE GS COMM OVERLAP", "SPLIT")) {
     if ((rc = ellipticAx<T>(elliptic, mesh->NglobalGatherElements, mesh->o_globalGatherElementList.p, o_q, o_Aq)))
       return rc;
     if (masked && elliptic->NmaskedGlobal)
@@ -296,13 +300,8 @@ int ellipticOperator(elliptic_t* elliptic, const T* o_q, T* o_Aq, bool masked, A
                            masked ? elliptic->NmaskedLocal : 0, elliptic->o_maskIdsLocal.p, elliptic->stream);
   }
   if ((rc = ellipticAxDot<T>(elliptic, mesh->Nelements, mesh->o_elementList.p, o_q, o_Aq, dot))) return rc;
-  if (oogs->ogs->NhaloGather) {
-    // halo rows are packed from masked values: mask first
-    if (nm)
-      if ((rc = mask_launch<T>(nm, elliptic->o_maskIds.p, o_Aq, elliptic->stream))) return rc;
-    return oogs->startFinish<T>(o_Aq, elliptic->Nfields, elliptic->fieldOffset, gs_op::add, 0, nullptr,
-                                elliptic->stream);
-  }
+  // (masked nodes carry id 0 in the masked handle: they belong to no row, on-rank or halo, so zeroing them commutes
+  // with every sum and rides along in the gather-scatter launch)
   return oogs->startFinish<T>(o_Aq, elliptic->Nfields, elliptic->fieldOffset, gs_op::add, nm, elliptic->o_maskIds.p,
                               elliptic->stream);
 }
@@ -530,7 +529,7 @@ int ellipticSolveSetup(elliptic_t* elliptic)
 
   // ENABLE GS COMM OVERLAP: the reference times both variants and keeps the faster
   // (ellipticSetup.cpp:278-302).  Splitting only pays when there are halo rows.
-  elliptic->fusedHaloAx = !options.compareArgs("FUSED HALO AX", "FALSE");
+  elliptic->fusedHaloAx = !options.compareArgs("FUSED HALO AX", "FALSE") && getenv("NRSB_NO_FUSED_HALO") == nullptr;
   // measured (tools/gs_timing.py, B200): phase 2 with 192 threads per SM needs 15 us for the rows the separate
   // 2048-threads-per-SM kernel does in 12.5 us (both bound by LSU wavefronts of the scattered 8-byte accesses),
   // 42.0 vs 39.4 us per operator at E=4096: off unless asked for

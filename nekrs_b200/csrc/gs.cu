@@ -246,6 +246,140 @@ int gs_rows_launch(const GsRowsDev& R, int Nfields, dlong stride, T* q, cudaStre
   NRSB_CUDA(launch_pdl_consumer(kern, grid, dim3(kGsBS), 0, stream, R, G, stride, q));
   return NRSB_OK;
 }
+// ---- the whole oogs::startFinish (oogs.cpp:823-837: packBuf, exchange, gatherScatterMany, unpackBuf) for one field and
+// ogsAdd in ONE launch.  The reference needs pack kernel -> device sync -> MPI_Isend/Irecv/Waitall -> unpack kernel;
+// the fence + epoch-flag version of this file needs two launches and a system-scope fence (measured: ~15 us per
+// exchange more than the single-rank gather-scatter, 50 exchanges per V-cycle).  Here every halo value travels WITH
+// its flag: an 8-byte NVLink store {fp32 value | 32-bit epoch} (fp64: two such words, low and high half), which is
+// single-copy atomic, so neither a fence nor a separate flag nor a second launch is needed.  One thread per halo row:
+//   partial sum of the local copies -> store to every sharer's window -> poll the own window for the sharers' words
+//   -> add in ascending rank order (own partial at its own position: identical bits on every rank) -> local copies.
+// The on-rank rows and the mask are the other block kinds of the same grid (halo blocks first: their stores leave
+// as early as possible).  Windows are double-buffered by epoch parity (a rank cannot be more than one exchange
+// ahead of a neighbour because it needs the neighbour's words of the current one).
+template <typename T>
+__device__ __forceinline__ void ll_store(void* win, const int slot, const T val, const unsigned epoch)
+{
+  volatile unsigned long long* w = (volatile unsigned long long*)win + 2 * (size_t)slot;
+  if constexpr (sizeof(T) == 4) {
+    w[0] = ((unsigned long long)epoch << 32) | (unsigned long long)__float_as_uint(val);
+  } else {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(val);
+    w[0] = ((unsigned long long)epoch << 32) | (b & 0xffffffffull);
+    w[1] = ((unsigned long long)epoch << 32) | (b >> 32);
+  }
+}
+template <typename T>
+__device__ __forceinline__ T ll_poll(const void* win, const int slot, const unsigned epoch, int* err)
+{
+  const volatile unsigned long long* w = (const volatile unsigned long long*)win + 2 * (size_t)slot;
+  const long long t0 = clock64();
+  unsigned long long a = w[0], b = 0;
+  if constexpr (sizeof(T) == 8) b = w[1];
+  while ((unsigned)(a >> 32) != epoch || (sizeof(T) == 8 && (unsigned)(b >> 32) != epoch)) {
+    if (clock64() - t0 > (1ll << 34)) {  // ~8 s: the peer never sent; flag it instead of hanging the box
+      if (err) *err = 1;
+      break;
+    }
+    a = w[0];
+    if constexpr (sizeof(T) == 8) b = w[1];
+  }
+  if constexpr (sizeof(T) == 4)
+    return __uint_as_float((unsigned)a);
+  else
+    return __longlong_as_double((long long)((a & 0xffffffffull) | (b << 32)));
+}
+
+template <typename T, int kRP>
+__global__ void __launch_bounds__(kGsBS, 2048 / kGsBS)
+    gs_exchange_ll_kernel(const GsRowsDev R, const GsGrid G, const int haloBlocks, const HaloExchangeDev H,
+                          T* __restrict__ v)
+{
+  pdl_trigger();
+  if ((int)blockIdx.x >= haloBlocks) {
+    gs_rows_body<T, kRP>(R, G, blockIdx.x - haloBlocks, v);
+    return;
+  }
+  const int row = blockIdx.x * kGsBS + threadIdx.x;
+  if (row >= H.nRows) return;
+  const int4 rl = H.rowLocal[row];  // {id0, id1 | -1, local copies, -}
+  const int4 rs = H.rowSend[row];   // {peer, slot, destinations, -}
+  const int4 rf = H.recvFlat[row];  // {slot a, slot b, own position, contributions | -1}
+  pdl_wait();
+  // own partial: local copies in ascending local index
+  T own;
+  if (rl.z <= 2) {
+    own = v[rl.x];
+    if (rl.y >= 0) own += v[rl.y];
+  } else {
+    const int s0 = H.rowStarts[row], s1 = H.rowStarts[row + 1];
+    own = v[H.rowIds[s0]];
+    for (int c = s0 + 1; c < s1; ++c) own += v[H.rowIds[c]];
+  }
+  // push to every sharer
+  if (rs.z == 1) {
+    ll_store<T>(H.peerWindowInline[rs.x], rs.y, own, H.epoch32);
+  } else {
+    for (int d = H.sendStarts[row]; d < H.sendStarts[row + 1]; ++d) {
+      const int p = H.sendPeer[d];
+      ll_store<T>(H.peerWindowInline[p], (int)H.peerRemoteOffset[p] + H.sendSlot[d], own, H.epoch32);
+    }
+  }
+  // receive and fold in ascending rank order
+  T tot;
+  if (rf.w == 2) {
+    const T a = ll_poll<T>(H.myLL, rf.x, H.epoch32, H.err);
+    tot = (rf.z == 0) ? own + a : a + own;
+  } else if (rf.w == 3) {
+    const T a = ll_poll<T>(H.myLL, rf.x, H.epoch32, H.err);
+    const T b = ll_poll<T>(H.myLL, rf.y, H.epoch32, H.err);
+    const T c0 = (rf.z == 0) ? own : a;
+    const T c1 = (rf.z == 0) ? a : (rf.z == 1 ? own : b);
+    const T c2 = (rf.z == 2) ? own : b;
+    tot = (c0 + c1) + c2;
+  } else {
+    tot = T(0);
+    bool first = true;
+    for (int c = H.recvStarts[row]; c < H.recvStarts[row + 1]; ++c) {
+      const int p = H.recvPeer[c];
+      const T val = (p < 0) ? own : ll_poll<T>(H.myLL, (int)H.peerRecvOffset[p] + H.recvSlot[c], H.epoch32, H.err);
+      tot = first ? val : tot + val;
+      first = false;
+    }
+  }
+  if (rl.z <= 2) {
+    v[rl.x] = tot;
+    if (rl.y >= 0) v[rl.y] = tot;
+  } else {
+    for (int c = H.rowStarts[row]; c < H.rowStarts[row + 1]; ++c) v[H.rowIds[c]] = tot;
+  }
+}
+
+template <typename T>
+int gs_exchange_ll_launch(const GsRowsDev& R, const HaloExchangeDev& H, T* v, cudaStream_t stream)
+{
+  auto blocks = [](long n, long per) { return (int)((n + per - 1) / per); };
+  GsGrid G;
+  G.quadBlocks = blocks(R.nQuads, kGsBS);
+  G.octBlocks = blocks(R.nOcts, kGsBS);
+  G.genBlocks = blocks(R.nGen, kGsBS);
+  G.maskBlocks = blocks(R.nMasked, (long)kGsBS * kGsMaskPerThread);
+  const int haloBlocks = blocks(H.nRows, kGsBS);
+  const long wave = (long)kNumSMs * (2048 / kGsBS);
+  const int rpMax = sizeof(T) == 8 ? 3 : 4;
+  int rp = 1;
+  const long others = (long)G.quadBlocks + G.octBlocks + G.genBlocks + G.maskBlocks + haloBlocks;
+  while (rp < rpMax && (long)blocks(R.nPairs, (long)kGsBS * rp) + others > wave) ++rp;
+  G.pairBlocks = blocks(R.nPairs, (long)kGsBS * rp);
+  const int localBlocks = G.pairBlocks + G.quadBlocks + G.octBlocks + G.genBlocks + G.maskBlocks;
+  auto kern = rp == 1 ? gs_exchange_ll_kernel<T, 1> : rp == 2 ? gs_exchange_ll_kernel<T, 2>
+                      : rp == 3 ? gs_exchange_ll_kernel<T, 3> : gs_exchange_ll_kernel<T, 4>;
+  NRSB_CUDA(launch_pdl_consumer(kern, dim3(localBlocks + haloBlocks), dim3(kGsBS), 0, stream, R, G, haloBlocks, H, v));
+  return NRSB_OK;
+}
+template int gs_exchange_ll_launch<double>(const GsRowsDev&, const HaloExchangeDev&, double*, cudaStream_t);
+template int gs_exchange_ll_launch<float>(const GsRowsDev&, const HaloExchangeDev&, float*, cudaStream_t);
+
 template <typename T>
 int gs_rows_halo_launch(const GsRowsDev& R, const HaloExchangeDev& H, const T* partial, T* v, cudaStream_t stream)
 {

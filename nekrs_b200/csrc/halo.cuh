@@ -46,11 +46,19 @@ struct HaloExchangeDev {
   int myRank;
   unsigned long long epoch;
   int* err;  // host-mapped word: set when a wait for a peer timed out (checked by the host at its next sync)
+  // one-launch exchange (gs_exchange_ll_kernel): flag-in-data windows, 16 bytes per slot, this parity; the peers'
+  // windows come in peerWindowInline (<= kInlinePeers peers)
+  const int4* rowSend;  // per halo row {peer, absolute slot in the peer window, number of destinations, 0}
+  void* const* peerLL;
+  void* myLL;
+  unsigned epoch32;
 };
 
 struct GsRowsDev;
 template <typename T>
 int gs_rows_halo_launch(const GsRowsDev& R, const HaloExchangeDev& H, const T* partial, T* v, cudaStream_t stream);
+template <typename T>
+int gs_exchange_ll_launch(const GsRowsDev& R, const HaloExchangeDev& H, T* v, cudaStream_t stream);
 
 template <typename T>
 __device__ __forceinline__ T gs_combine(T a, T b, gs_op op)

@@ -135,10 +135,15 @@ class oogs_t {
   // start() without the pack launch: advances the epoch and describes the exchange to a kernel that
   // performs the pack itself once `NhaloElements` more elements have been counted (struct FusedHalo, halo.cuh)
   int begin_fused(struct FusedHalo* F, dlong NhaloElements, dlong stride);
+  // one-launch exchange with flag-in-data windows (one field, ogsAdd); returns 1 when the case is not covered
+  template <typename T>
+  int exchange_ll(T* v, int k, gs_op op, dlong Nmasked, const dlong* maskIds, cudaStream_t stream);
   template <typename T>
   int startFinish(T* v, int k, dlong stride, gs_op op, dlong Nmasked, const dlong* maskIds, cudaStream_t stream)
   {
-    int rc = start(v, k, stride, op, stream);
+    int rc = exchange_ll<T>(v, k, op, Nmasked, maskIds, stream);
+    if (rc != 1) return rc;
+    rc = start(v, k, stride, op, stream);
     if (rc) return rc;
     return finish(v, k, stride, op, Nmasked, maskIds, stream);
   }

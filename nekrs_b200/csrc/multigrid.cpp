@@ -12,6 +12,8 @@
 // is implemented literally.
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 
@@ -854,19 +856,71 @@ int MGSolver_t::runAdditiveVcycle()
   return NRSB_OK;
 }
 
+// developer aid (NRSB_MG_TIMING=1): CUDA-event time per V-cycle phase and level, printed every 32 cycles
+namespace {
+struct MgTimer {
+  bool on = getenv("NRSB_MG_TIMING") != nullptr;
+  std::vector<cudaEvent_t> ev;
+  std::vector<std::string> label;
+  std::map<std::string, double> acc;
+  int cycles = 0;
+  void mark(const std::string& what, cudaStream_t st)
+  {
+    if (!on) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    ev.push_back(e);
+    label.push_back(what);
+  }
+  void flush(int rank)
+  {
+    if (!on || ev.empty()) return;
+    cudaEventSynchronize(ev.back());
+    for (size_t i = 1; i < ev.size(); ++i) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
+      acc[label[i]] += ms;
+    }
+    for (auto e : ev) cudaEventDestroy(e);
+    ev.clear();
+    label.clear();
+    if (++cycles % 32 == 0) {
+      fprintf(stderr, "[rank %d] V-cycle phases, mean us per cycle over %d cycles:", rank, cycles);
+      for (auto& kv : acc) fprintf(stderr, "  %s %.1f", kv.first.c_str(), kv.second / cycles * 1e3);
+      fprintf(stderr, "\n");
+    }
+  }
+};
+MgTimer g_mgTimer;
+}  // namespace
+
 int MGSolver_t::runVcycle(int k)
 {
   pMGLevel* level = levels[k].get();
   float *o_rhs = level->o_rhs, *o_x = level->o_x, *o_res = level->o_res.p;
-  if (k == baseLevel) return coarseSolve(o_rhs, o_x);
+  cudaStream_t st = level->elliptic->stream;
+  const std::string L = "L" + std::to_string(k) + ":";
+  if (k == 0) g_mgTimer.mark("start", st);
+  if (k == baseLevel) {
+    const int rc = coarseSolve(o_rhs, o_x);
+    g_mgTimer.mark("coarse", st);
+    return rc;
+  }
   pMGLevel* levelC = levels[k + 1].get();
   int rc;
   if ((rc = level->smooth(o_rhs, o_x, true))) return rc;
+  g_mgTimer.mark(L + "smoothDown", st);
   if ((rc = level->residual(o_rhs, o_x, o_res))) return rc;
   if ((rc = levelC->coarsen(o_res, levelC->o_rhs))) return rc;
+  g_mgTimer.mark(L + "resid+coarsen", st);
   if ((rc = runVcycle(k + 1))) return rc;
   if ((rc = levelC->prolongate(levelC->o_x, o_x))) return rc;
-  return level->smooth(o_rhs, o_x, false);
+  g_mgTimer.mark(L + "prolong", st);
+  rc = level->smooth(o_rhs, o_x, false);
+  g_mgTimer.mark(L + "smoothUp", st);
+  if (k == 0) g_mgTimer.flush(level->elliptic->comm ? level->elliptic->comm->rank : 0);
+  return rc;
 }
 
 // ------------------------------------------------------------------------------------------

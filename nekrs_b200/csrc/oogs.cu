@@ -202,6 +202,13 @@ struct oogs_dev_t {
   void* arena = nullptr;
   std::vector<void*> peerArena;  // IPC-opened
   size_t windowBytes = 0;
+  // flag-in-data windows of the one-launch exchange (gs.cu gs_exchange_ll_kernel): 16 bytes per slot, two parities,
+  // behind the flags in the same arena (one IPC handle)
+  size_t llOffset = 0, llBytes = 0;
+  std::vector<void*> h_peerLL[2];
+  dbuf<void*> d_peerLL[2];
+  dbuf<int4> rowSend;  // per halo row {peer, absolute slot in the peer window, number of destinations, 0}
+  unsigned long long epochLL = 0;
 };
 static std::map<oogs_t*, std::unique_ptr<oogs_dev_t>> g_dev;
 
@@ -275,7 +282,9 @@ int oogs_t::setup(ogs_t* ogs_, comm_t* comm_, int maxFields_)
   auto dev = std::make_unique<oogs_dev_t>();
   // arena = [window parity 0][window parity 1][flags nranks]
   dev->windowBytes = ((windowSlots * maxFields * sizeof(double) + 255) / 256) * 256;
-  const size_t arenaBytes = 2 * dev->windowBytes + sizeof(unsigned long long) * nranks * kFlagSlots;
+  dev->llOffset = ((2 * dev->windowBytes + sizeof(unsigned long long) * nranks * kFlagSlots + 255) / 256) * 256;
+  dev->llBytes = ((windowSlots * 16 + 255) / 256) * 256;
+  const size_t arenaBytes = dev->llOffset + 2 * dev->llBytes;
   NRSB_CUDA(cudaMalloc(&dev->arena, arenaBytes));
   NRSB_CUDA(cudaMemset(dev->arena, 0, arenaBytes));
   NRSB_CUDA(cudaDeviceSynchronize());
@@ -309,6 +318,11 @@ int oogs_t::setup(ogs_t* ogs_, comm_t* comm_, int maxFields_)
   if ((rc = dev->peerRank.upload(prank))) return rc;
   dev->h_peerWindow[0] = win[0];
   dev->h_peerWindow[1] = win[1];
+  for (int par = 0; par < 2; ++par) {
+    for (auto& p : peers)
+      dev->h_peerLL[par].push_back((char*)dev->peerArena[p.rank] + dev->llOffset + (size_t)par * dev->llBytes);
+    if ((rc = dev->d_peerLL[par].upload(dev->h_peerLL[par]))) return rc;
+  }
   if ((rc = dev->d_peerWindow[0].upload(win[0]))) return rc;
   if ((rc = dev->d_peerWindow[1].upload(win[1]))) return rc;
   if ((rc = d_peerFlags.upload(pflags))) return rc;
@@ -383,6 +397,13 @@ int oogs_t::setup(ogs_t* ogs_, comm_t* comm_, int maxFields_)
     }
     if ((rc = dev->recvFlat.upload(rflat))) return rc;
     if ((rc = dev->rowLocal.upload(rloc))) return rc;
+    std::vector<int4> rsend(nRows);
+    for (int r = 0; r < nRows; ++r) {
+      const int d0 = sendStarts[r], nd = sendStarts[r + 1] - d0;
+      rsend[r] = make_int4(nd > 0 ? sendPeer[d0] : 0, nd > 0 ? (int)(peers[sendPeer[d0]].remoteOffset + sendSlot[d0]) : 0,
+                           nd, 0);
+    }
+    if ((rc = dev->rowSend.upload(rsend))) return rc;
   }
   if ((rc = d_sendStarts.upload(sendStarts))) return rc;
   if ((rc = d_sendPeer.upload(sendPeer))) return rc;
@@ -442,6 +463,10 @@ static HaloExchangeDev make_dev(oogs_t* o, oogs_dev_t* d, int parity)
   H.myRank = o->comm->rank;
   H.epoch = o->epoch;
   H.err = o->comm ? o->comm->d_err : nullptr;
+  H.rowSend = d->rowSend.p;
+  H.peerLL = nullptr;
+  H.myLL = nullptr;
+  H.epoch32 = 0;
   return H;
 }
 
@@ -522,6 +547,31 @@ int oogs_t::finish(T* v, int k, dlong stride, gs_op op, dlong Nmasked, const dlo
   NRSB_CHECK_LAUNCH();
   return NRSB_OK;
 }
+
+// oogs::startFinish for one field and ogsAdd in ONE launch with flag-in-data windows: see gs_exchange_ll_kernel
+// (gs.cu).  Returns 1 when the case is not covered (the caller then runs start + finish).
+template <typename T>
+int oogs_t::exchange_ll(T* v, int k, gs_op op, dlong Nmasked, const dlong* maskIds, cudaStream_t stream)
+{
+  static const bool off = getenv("NRSB_NO_LL_EXCHANGE") != nullptr;
+  if (off || !ogs || ogs->NhaloGather == 0 || k != 1 || op != gs_op::add || peers.size() > (size_t)kInlinePeers) return 1;
+  oogs_dev_t* d = g_dev[this].get();
+  ++d->epochLL;
+  if ((d->epochLL & 0xffffffffull) == 0) ++d->epochLL;  // 0 is "never written"
+  const int parity = (int)(d->epochLL & 1ull);
+  HaloExchangeDev H = make_dev(this, d, 0);
+  H.peerLL = d->d_peerLL[parity].p;
+  for (int p = 0; p < kInlinePeers; ++p)
+    H.peerWindowInline[p] = p < (int)d->h_peerLL[parity].size() ? d->h_peerLL[parity][p] : nullptr;
+  H.myLL = (char*)d->arena + d->llOffset + (size_t)parity * d->llBytes;
+  H.epoch32 = (unsigned)(d->epochLL & 0xffffffffull);
+  GsRowsDev R = ogs->rows;
+  R.nMasked = maskIds ? Nmasked : 0;
+  R.maskIds = maskIds;
+  return gs_exchange_ll_launch<T>(R, H, v, stream);
+}
+template int oogs_t::exchange_ll<double>(double*, int, gs_op, dlong, const dlong*, cudaStream_t);
+template int oogs_t::exchange_ll<float>(float*, int, gs_op, dlong, const dlong*, cudaStream_t);
 
 template int oogs_t::start<double>(double*, int, dlong, gs_op, cudaStream_t);
 template int oogs_t::start<float>(float*, int, dlong, gs_op, cudaStream_t);

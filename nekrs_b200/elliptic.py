@@ -124,6 +124,9 @@ class Elliptic:
         call("nrsb_elliptic_get_real", self._h, key.encode(), C.byref(v))
         return v.value
 
+    def set_real(self, key, value):
+        call("nrsb_elliptic_set_real", self._h, key.encode(), C.c_double(value))
+
     def get_array(self, key, dtype) -> np.ndarray:
         n = C.c_int64(0)
         call("nrsb_elliptic_get_array", self._h, key.encode(), None, C.c_int64(0), C.byref(n))

@@ -33,7 +33,7 @@ def run():
     x = np.zeros(n)
     ell.solve_host(rhs, x)
     h, hr = ell.res_history(), np.array(ref.res_history)
-    assert ell.Niter == ref.Niter and np.max(np.abs(h - hr) / hr) < 1e-8
+    assert ell.Niter == ref.Niter and np.max(np.abs(h - hr) / hr) < 1e-12
     # 3. BPS5: p-multigrid (RAS + 4th-kind Chebyshev) preconditioned FGMRES, iteration count vs oracle
     opts = pressure_options(**{"MULTIGRID SMOOTHER": "FOURTHOPTCHEBYSHEV+RAS"})
     ell2 = Elliptic(mesh, opts)

@@ -2,9 +2,10 @@
 PGMRES, Jacobi and p-multigrid preconditioners) against the oracle driver (oracle/driver.py = the
 reference's host control flow over the restated serial kernels), through the C ABI.
 
-Tolerances: fp64 operator 1e-12; per-iteration residual norms 1e-10 in the first iterations (round-off
-from FMA contraction / summation order is amplified by the Krylov recurrences afterwards); fp32
-multigrid kernels 1e-5; iteration counts +-1 (BASELINE.json north_star).
+Tolerances (BASELINE.json north_star): fp64 operator and EVERY per-iteration residual norm of the fp64 Krylov
+solvers 1e-12 (measured on B200: <= 4e-15 over 60 PCG iterations, with and without the q^T A q taken from the
+axhelm launch); the fp32 multigrid pieces what fp32 allows with the SAME lambda_max fed to both sides: smoother and
+V-cycle output 5e-6 (measured 1-4e-7), lambda_max itself 1e-6 (measured 4e-8); iteration counts equal.
 """
 import numpy as np
 import pytest
@@ -146,9 +147,14 @@ def test_bp5_pcg_residual_history(case_bp5):
     assert it == ref.Niter == 60          # tol 1e-15 is never reached: fixed work (kershaw.udf:47-53)
     h, hr = ell.res_history(), np.array(ref.res_history)
     assert abs(ell.res0Norm - ref.res0Norm) / ref.res0Norm < 1e-13
-    assert np.max(np.abs(h[:5] - hr[:5]) / hr[:5]) < 1e-10
-    assert np.max(np.abs(h - hr) / hr) < 1e-6
-    assert relerr(d_x.download()[:n], x_ref) < 1e-7
+    assert np.max(np.abs(h - hr) / hr) < 1e-12           # all 60 iterations (measured: 3.4e-15)
+    assert relerr(d_x.download()[:n], x_ref) < 1e-12
+    # the same with the reference's separate weighted-inner-product pass for p^T A p (PCG.cpp:150-157)
+    opts2 = dict(ell.options, **{"FUSED DOT AX": "FALSE"})
+    ell2 = Elliptic(mesh, opts2)
+    x2 = np.zeros(n)
+    ell2.solve_host(rhs, x2)
+    assert np.max(np.abs(ell2.res_history() - hr) / hr) < 1e-12
 
 
 @pytest.mark.parametrize("solver", ["PCG", "PCG+FLEXIBLE", "PGMRES", "PGMRES+FLEXIBLE"])
@@ -196,8 +202,9 @@ def test_multigrid_setup_and_components(orc, smoother):
         assert np.array_equal(ell.get_array("level%d:invDegree" % k, np.float64), L.ell.inv_degree)
         if not L.has_smoother:
             continue
-        # lambda_max estimate of S*A: same Arnoldi, fp32 operator inside -> 1e-4
-        assert abs(ell.get_real("level%d:maxEig" % k) - L.max_eig_value) / L.max_eig_value < 2e-4
+        # lambda_max estimate of S*A: same Arnoldi from the same start vector, fp32 operator inside (measured 4e-8)
+        assert abs(ell.get_real("level%d:maxEig" % k) - L.max_eig_value) / L.max_eig_value < 1e-6
+        ell.set_real("level%d:maxEig" % k, L.max_eig_value)   # from here on both sides use the SAME bound
         n = L.Nrows
         u = rng.random(n).astype(np.float32)
         u[L.ell.mask_ids] = 0
@@ -218,11 +225,10 @@ def test_multigrid_setup_and_components(orc, smoother):
         rhs = rng.random(n).astype(np.float32)
         rhs[L.ell.mask_ids] = 0
         ref_x = np.zeros(n, np.float32)
-        # use the oracle's own lambda for the oracle and the product's for the product: they agree to 2e-4
         L.smooth(rhs.copy(), ref_x, True)
         d_x = DB.zeros(n, np.float32)
         ell.level_op(k, "smooth", DB(like=rhs), d_x)
-        assert relerr(d_x.download(), ref_x) < 5e-4
+        assert relerr(d_x.download(), ref_x) < 5e-6            # measured 1-4e-7
 
 
 @pytest.mark.parametrize("N,nel,smoother,extra", [
@@ -244,7 +250,7 @@ def test_bps5_iteration_parity(orc, N, nel, smoother, extra):
     assert it < int(opts["MAXIMUM ITERATIONS"])
     h, hr = ell.res_history(), np.array(ref.res_history)
     k = min(len(h), len(hr), 4)
-    assert np.max(np.abs(h[:k] - hr[:k]) / hr[:k]) < 5e-3      # fp32 V-cycle inside
+    assert np.max(np.abs(h[:k] - hr[:k]) / hr[:k]) < 1e-4      # fp32 V-cycle inside (measured <= 4e-6)
     assert ell.resNorm <= 1e-8 * ell.res0Norm * 1.0000001
     assert relerr(x, x_ref) < 1e-6
 
@@ -258,9 +264,12 @@ def test_preconditioner_vcycle_output(orc):
     z_ref = np.zeros(n)
     ref.preconditioner(r, z_ref)
     d_z = DB.zeros(ell.fieldOffset, np.float64)
+    for k, L in enumerate(ref.levels):
+        if L.has_smoother:
+            ell.set_real("level%d:maxEig" % k, L.max_eig_value)   # same Chebyshev bounds on both sides
     ell.preconditioner(DB(like=padded(r, ell.fieldOffset)), d_z)
-    assert relerr(d_z.download()[:n], z_ref) < 2e-4
-    assert abs(ell.get_int("coarseIterations") - ref.coarse.last_iter) <= 8
+    assert relerr(d_z.download()[:n], z_ref) < 5e-6               # measured 8e-8
+    assert ell.get_int("coarseIterations") == ref.coarse.last_iter
 
 
 @pytest.mark.parametrize("smoother", ["RAS", "ASM"])
@@ -279,7 +288,7 @@ def test_additive_vcycle(orc, smoother):
     ref.preconditioner(r, z_ref)
     d_z = DB.zeros(ell.fieldOffset, np.float64)
     ell.preconditioner(DB(like=padded(r, ell.fieldOffset)), d_z)
-    assert relerr(d_z.download()[:n], z_ref) < 2e-4
+    assert relerr(d_z.download()[:n], z_ref) < 5e-6
     rhs = meshgen.kershaw_rhs(mesh)
     x_ref = ref.solve(rhs, np.zeros(n))
     x = np.zeros(n)

@@ -83,6 +83,9 @@ def run_kershaw(dist, rank, world, local, n=20, N=7, reps=5, bp5_iters=1000, smo
         ell.destroy()
     if not skip_bps5:
         opts = pressure_options(**{"MULTIGRID SMOOTHER": smoother, "COARSE SOLVER TOLERANCE": coarse_tol})
+        for kv in os.environ.get("NRSB_EXTRA_OPTS", "").split(";"):  # developer aid: KEY=VALUE;KEY=VALUE
+            if "=" in kv:
+                opts[kv.split("=", 1)[0].strip().upper()] = kv.split("=", 1)[1].strip()
         ts = time.time()
         ell = Elliptic(mesh, opts, comm=comm, topo_of=topo_of)
         setup_s = time.time() - ts
