@@ -134,7 +134,11 @@ def test_fullsize_bp5_history(full):
     it = ell.solve_host(rhs, x)
     h, hr = ell.res_history(), np.array(ref.res_history)
     assert it == ref.Niter == 30
-    assert np.max(np.abs(h - hr) / hr) < 1e-12
+    # 4.1 M nodes: the oracle's norm is ONE sequential fp64 sum (linAlg serial kernels), the device's a tree; the two
+    # differ by a constant 3e-12 relative from the first iteration on (the recurrences themselves agree: the offset
+    # does not grow over the 30 iterations).  On the 18-element mesh of test_gpu_elliptic.py the bound is 1e-12.
+    d = np.abs(h - hr) / hr
+    assert d.max() < 2e-11 and abs(d[-1] - d[0]) < 1e-12
 
 
 def test_fullsize_fdm(orc):
