@@ -529,7 +529,10 @@ int ellipticSolveSetup(elliptic_t* elliptic)
 
   // ENABLE GS COMM OVERLAP: the reference times both variants and keeps the faster
   // (ellipticSetup.cpp:278-302).  Splitting only pays when there are halo rows.
-  elliptic->fusedHaloAx = !options.compareArgs("FUSED HALO AX", "FALSE") && getenv("NRSB_NO_FUSED_HALO") == nullptr;
+  // Measured (2 B200, E = 4096 per GPU, N = 7 fp64): Ax on all 148 SMs + the one-launch flag-in-data exchange
+  // 41.1 us per operator, the single launch with 8 pusher CTAs + finish 41.8 us (and the pushers take 15-16 SMs on
+  // 4 and 8 GPUs): the in-kernel push is opt-in (FUSED HALO AX = TRUE) since the exchange became one launch.
+  elliptic->fusedHaloAx = options.compareArgs("FUSED HALO AX", "TRUE") || getenv("NRSB_FUSED_HALO") != nullptr;
   // measured (tools/gs_timing.py, B200): phase 2 with 192 threads per SM needs 15 us for the rows the separate
   // 2048-threads-per-SM kernel does in 12.5 us (both bound by LSU wavefronts of the scattered 8-byte accesses),
   // 42.0 vs 39.4 us per operator at E=4096: off unless asked for

@@ -589,7 +589,7 @@ int comm_setup_reduce(comm_t* c)
     *c->h_err = 0;
     NRSB_CUDA(cudaHostGetDevicePointer((void**)&c->d_err, c->h_err, 0));
   }
-  const size_t slotDoubles = (size_t)2 * c->nranks * kMaxRed;
+  const size_t slotDoubles = (size_t)2 * c->nranks * kMaxRed * 2;  // 16 bytes per value: flag-in-data words
   // one arena so that a single IPC handle covers slots and flags
   if ((rc = c->redSlots.alloc(slotDoubles + c->nranks))) return rc;
   if ((rc = c->redEpoch.alloc(1))) return rc;

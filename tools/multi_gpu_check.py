@@ -74,7 +74,8 @@ def main():
     nloc = part.Nelements * Np
 
     # ---- fused operator + BP5
-    opts = {"SOLVER": "PCG", "PRECONDITIONER": "NONE", "MAXIMUM ITERATIONS": "40", "SOLVER TOLERANCE": "1e-15"}
+    opts = {"SOLVER": "PCG", "PRECONDITIONER": "NONE", "MAXIMUM ITERATIONS": "40", "SOLVER TOLERANCE": "1e-15",
+            "FUSED HALO AX": "TRUE"}  # the in-kernel halo push (opt-in); the default path is checked below
     ell = Elliptic(part, opts, comm=comm, topo_of=topo_of)
     ref = driver.OSolver(whole, opts, orc)
     report("halo rows present", ell.get_int("NhaloGather") > 0, "NhaloGather=%d overlap=%d" % (
@@ -111,8 +112,7 @@ def main():
     ell_split.destroy()
     # the unsplit operator: Ax on all elements + the one-launch flag-in-data exchange (oogs_t::exchange_ll)
     opts_ll = dict(opts)
-    opts_ll["FUSED HALO AX"] = "FALSE"
-    opts_ll["ENABLE GS COMM OVERLAP"] = "TRUE"
+    del opts_ll["FUSED HALO AX"]  # library defaults
     ell_ll = Elliptic(part, opts_ll, comm=comm, topo_of=topo_of)
     d_Aq3 = DB.zeros(ell.fieldOffset, np.float64)
     for rep in range(5):
