@@ -110,6 +110,15 @@ int nrsb_adyMany(int precision, nrsb_dlong N, int Nfields, nrsb_dlong offset, do
 int nrsb_axdy(int precision, nrsb_dlong N, double alpha, const void* d_x, void* d_y, void* stream);
 int nrsb_axpbyzMany(int precision, nrsb_dlong N, int Nfields, nrsb_dlong offset, double alpha, const void* d_x,
                     double beta, const void* d_y, void* d_z, void* stream);
+/* ellipticBlockPartialAxCoeffHex3D (kernels/elliptic/ellipticBlockPartialAxCoeffHex3D.okl, serial twin .c:2-152;
+ * registered for the velocity solve, registerEllipticKernels.cpp): three Helmholtz operators sharing ggeo,
+ * Aq[id + f*offset] = (D^T lambda0_f G D + lambda1_f GwJ) q[id + f*offset], f = 0..2; coefficients at
+ * lambda[p_lambda*id + f*loffset] (lambdaField = p_lambda).  The fields of an element run as neighbouring blocks, so
+ * the geometric factors cross HBM once. */
+int nrsb_ellipticBlockPartialAxCoeffHex3D(int Nq, int precision, nrsb_dlong Nelements, nrsb_dlong offset,
+                                          nrsb_dlong loffset, const nrsb_dlong* d_elementList, const void* d_ggeo,
+                                          const void* D_host, const void* d_lambda0, const void* d_lambda1,
+                                          int lambdaField, const void* d_q, void* d_Aq, void* stream);
 /* ellipticBlockBuildDiagonalHex3D (kernels/elliptic/ellipticBlockBuildDiagonalHex3D.okl; ellipticUpdateJacobi.cpp:
  * 38-47,66-75): Aq[id + l*offset] = diag(D^T lambda0 G D)[id] (+ lambda1 GwJ), l < Nfields.  lambdaField = 1:
  * lambda0/lambda1 are per-node fields read at id + l*loffset (the reference's layout), 0: one value each.

@@ -296,7 +296,10 @@ __global__ void __launch_bounds__(NGROUPS* Nq* Nq + 32, 1)
       const long long t0 = clock64();
       while (ld_acquire_u64(F.counter) < F.target) {
         __nanosleep(64);
-        if (clock64() - t0 > (1ll << 33)) break;  // ~4 s: never reached unless co-residency was violated
+        if (clock64() - t0 > (1ll << 33)) {  // ~4 s: co-residency of the grid was violated (MPS / MIG / a smaller part)
+          if (F.err) *F.err = 1;               // the host turns this into NRSB_ERR_CUDA at its next synchronisation
+          break;
+        }
       }
     }
     __syncthreads();
@@ -517,7 +520,10 @@ __global__ void __launch_bounds__(NGROUPS* Nq* Nq + 32, 1)
       const long long t0 = clock64();
       while (ld_acquire_u64(R2.arrive) < R2.target) {
         __nanosleep(32);
-        if (clock64() - t0 > (1ll << 33)) break;  // ~4 s: never reached unless co-residency was violated
+        if (clock64() - t0 > (1ll << 33)) {  // ~4 s: co-residency of the grid was violated
+          if (R2.err) *R2.err = 1;
+          break;
+        }
       }
     }
     group_sync(15, nConsumers);

@@ -371,6 +371,23 @@ int nrsb_axpbyzMany(int precision, nrsb_dlong N, int Nfields, nrsb_dlong offset,
                         : axpbyz_many_launch<float>(N, Nfields, offset, (float)alpha, (const float*)d_x, (float)beta,
                                                     (const float*)d_y, (float*)d_z, ST(stream));
 }
+int nrsb_ellipticBlockPartialAxCoeffHex3D(int Nq, int precision, nrsb_dlong Nelements, nrsb_dlong offset,
+                                          nrsb_dlong loffset, const nrsb_dlong* d_elementList, const void* d_ggeo,
+                                          const void* D_host, const void* d_lambda0, const void* d_lambda1,
+                                          int lambdaField, const void* d_q, void* d_Aq, void* stream)
+{
+  PREC_OK(precision);
+  NRSB_REQUIRE(D_host && (Nelements == 0 || (d_elementList && d_ggeo && d_lambda0 && d_lambda1 && d_q && d_Aq)),
+               "NULL argument");
+  const int variant = 1;
+  return precision == 8
+             ? ax_block_launch<double>(Nq, variant, Nelements, 3, offset, loffset, d_elementList, (const double*)d_ggeo,
+                                       (const double*)D_host, (const double*)d_lambda0, (const double*)d_lambda1,
+                                       lambdaField, (const double*)d_q, (double*)d_Aq, ST(stream))
+             : ax_block_launch<float>(Nq, variant, Nelements, 3, offset, loffset, d_elementList, (const float*)d_ggeo,
+                                      (const float*)D_host, (const float*)d_lambda0, (const float*)d_lambda1,
+                                      lambdaField, (const float*)d_q, (float*)d_Aq, ST(stream));
+}
 int nrsb_ellipticBlockBuildDiagonalHex3D(int Nq, int precision, nrsb_dlong Nelements, int Nfields, nrsb_dlong offset,
                                          nrsb_dlong loffset, const void* d_ggeo, const void* D_host,
                                          const void* d_lambda0, const void* d_lambda1, int poisson, int lambdaField,

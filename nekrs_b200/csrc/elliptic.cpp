@@ -33,6 +33,7 @@ elliptic_t::elliptic_t() {}
 elliptic_t::~elliptic_t()
 {
   if (h_scal) cudaFreeHost(h_scal);
+  if (h_err) cudaFreeHost(h_err);
 }
 
 int elliptic_t::read_scalars(int first, int count, double* out)
@@ -42,6 +43,11 @@ int elliptic_t::read_scalars(int first, int count, double* out)
   for (int i = 0; i < count; ++i) out[i] = h_scal[first + i];
   if (comm && comm->peer_timeout()) {
     set_last_error("a device-side wait for a peer rank timed out (halo flags / all-reduce): a rank is missing");
+    return NRSB_ERR_CUDA;
+  }
+  if (h_err && *h_err) {
+    set_last_error("a device-wide wait inside a fused launch timed out: its CTAs were not co-resident (MPS / MIG / "
+                   "fewer SMs than the launch assumes); results of that launch are invalid");
     return NRSB_ERR_CUDA;
   }
   return NRSB_OK;
@@ -213,6 +219,7 @@ int ellipticOperator(elliptic_t* elliptic, const T* o_q, T* o_Aq, bool masked, A
     FR.R.nMasked = nm;
     FR.R.maskIds = elliptic->o_maskIds.p;
     FR.arrive = elliptic->fusedArrive.p;
+    FR.err = elliptic->d_err;
     FR.target = elliptic->fusedArriveTarget;
   }
   if (gsInLaunch && oogs->ogs->NhaloGather == 0) {
@@ -233,6 +240,7 @@ int ellipticOperator(elliptic_t* elliptic, const T* o_q, T* o_Aq, bool masked, A
     // so it commutes with every sum).
     FusedHalo F;
     if ((rc = oogs->begin_fused(&F, mesh->NglobalGatherElements, elliptic->fieldOffset))) return rc;
+    F.err = elliptic->d_err;
     // developer aid (NRSB_OP_TIMING=1): per-kernel times of the pipelined operator, no host sync per step
     static const bool timing = getenv("NRSB_OP_TIMING") != nullptr;
     static std::vector<cudaEvent_t> ev;
@@ -445,6 +453,11 @@ int elliptic_workspace(elliptic_t* elliptic)
   if (elliptic->comm && elliptic->comm->nranks > 1) elliptic->ws.peer = elliptic->comm->peerReduce();
   if ((rc = elliptic->o_scal.alloc(S_COUNT))) return rc;
   if (!elliptic->h_scal) NRSB_CUDA(cudaMallocHost((void**)&elliptic->h_scal, sizeof(double) * S_COUNT));
+  if (!elliptic->h_err) {
+    NRSB_CUDA(cudaHostAlloc((void**)&elliptic->h_err, sizeof(int), cudaHostAllocMapped));
+    *elliptic->h_err = 0;
+    NRSB_CUDA(cudaHostGetDevicePointer((void**)&elliptic->d_err, elliptic->h_err, 0));
+  }
   return NRSB_OK;
 }
 
@@ -538,6 +551,14 @@ int ellipticSolveSetup(elliptic_t* elliptic)
   // 42.0 vs 39.4 us per operator at E=4096: off unless asked for
   elliptic->fusedGsAx = options.compareArgs("FUSED GS AX", "TRUE") || getenv("NRSB_FUSED_GS") != nullptr;
   elliptic->fusedDotAx = !options.compareArgs("FUSED DOT AX", "FALSE") && getenv("NRSB_NO_FUSED_DOT") == nullptr;
+  {
+    // the fused launches are persistent grids of kNumSMs co-resident CTAs that wait for each other: only on a device
+    // that really has that many SMs to itself
+    int dev = 0, sms = 0;
+    NRSB_CUDA(cudaGetDevice(&dev));
+    NRSB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (sms < kNumSMs) elliptic->fusedHaloAx = elliptic->fusedGsAx = false;
+  }
   elliptic->overlap = elliptic->ogs->NhaloGather > 0 && !options.compareArgs("ENABLE GS COMM OVERLAP", "FALSE") &&
                       mesh->NlocalGatherElements > 0;
 

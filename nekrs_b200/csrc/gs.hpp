@@ -35,6 +35,7 @@ struct FusedRows {
   // product  sum invDegree * q * (Q Q^T A_L q)  that PCG.cpp:150-157 computes with a separate pass after the
   // gather-scatter.
   double* dotPartials = nullptr;
+  int* err = nullptr;  // host-mapped error word: the device-wide wait of the launch gave up
 };
 
 template <typename T>

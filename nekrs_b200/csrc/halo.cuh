@@ -206,6 +206,7 @@ struct FusedHalo {
   // developer aid (NRSB_OP_TIMING): globaltimer stamps, [0..4] pusher 0 (start, halo elements stored, pushed,
   // fenced, flags raised), [8] first / [9] last axhelm CTA done
   unsigned long long* stamps = nullptr;
+  int* err = nullptr;  // host-mapped error word: a bounded wait of this launch gave up
 };
 
 }  // namespace nrsb

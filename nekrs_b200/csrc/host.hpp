@@ -359,6 +359,10 @@ class elliptic_t {
   ReduceWs ws;
   dbuf<double> o_scal;       // device scalars
   double* h_scal = nullptr;  // pinned mirror
+  // host-mapped error word of this handle: a bounded device-side wait that gave up sets it (fused launches whose
+  // grid was not co-resident); read_scalars and the solve entry points turn it into NRSB_ERR_CUDA
+  int* h_err = nullptr;
+  int* d_err = nullptr;
   // Krylov
   int ax_variant[2] = {-1, -1};  // [0] fp64, [1] fp32
   std::unique_ptr<precon_t> precon;

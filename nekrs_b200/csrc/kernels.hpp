@@ -15,6 +15,10 @@ template <typename T>
 int ax_launch(int Nq, int variant, dlong Nelements, dlong loffset, const dlong* elementList, const T* ggeo,
               const T* D_host, const T* lambda0, const T* lambda1, int poisson, int lambdaField, const T* q, T* Aq,
               cudaStream_t stream, AxDot* dot = nullptr);
+template <typename T>
+int ax_block_launch(int Nq, int variant, dlong Nelements, int Nfields, dlong offset, dlong loffset,
+                    const dlong* elementList, const T* ggeo, const T* D_host, const T* lambda0, const T* lambda1,
+                    int lambdaField, const T* q, T* Aq, cudaStream_t stream);
 int ax_default_variant(int Nq, int precision);
 struct FusedHalo;
 template <typename T>

@@ -107,11 +107,7 @@ int pMGLevel::coarsen(float* x, float* Rx)
   // x *= invDegreeFine  (paxmy, :46)
   if ((rc = axmyz_launch<float>((long)mesh->Nelements * NpF, 1.0f, o_invDegreeFine, x, x, st))) return rc;
   if ((rc = transfer_dispatch(true, NqF, mesh->Nq, mesh->Nelements, R.data(), x, Rx, st))) return rc;
-  // gather-scatter + mask again (coarsen does not preserve the mask)
-  if (elliptic->oogs->ogs->NhaloGather) {
-    if ((rc = elliptic->oogs->startFinish<float>(Rx, 1, 0, gs_op::add, 0, nullptr, st))) return rc;
-    return ellipticApplyMask<float>(elliptic, Rx);
-  }
+  // gather-scatter + mask again (coarsen does not preserve the mask; the mask rides along in the same launch)
   return elliptic->oogs->startFinish<float>(Rx, 1, 0, gs_op::add, elliptic->Nmasked, elliptic->o_maskIds.p, st);
 }
 
@@ -230,27 +226,15 @@ int pMGLevel::smoothSchwarz(const float* u, float* Su, bool /*xIsZero*/)
   int rc;
   if ((rc = pre_fdm_launch(mesh->Nq, E, u, o_work1.p, st))) return rc;
   if ((rc = ogsExt->startFinish<float>(o_work1.p, 1, 0, gs_op::add, 0, nullptr, st))) return rc;
+  // (masked nodes carry id 0 in the masked handle, i.e. belong to no on-rank or halo row: ellipticApplyMask commutes
+  // with the gather-scatter and rides along in its launch.  The reference splits fusedFDM into halo / interior
+  // elements around oogs::start / finish, ellipticMultiGridSchwarz.cpp:1086-1121; with the one-launch exchange the
+  // unsplit sequence has fewer launches and no fence.)
   if (options.compareArgs("MULTIGRID SMOOTHER", "RAS")) {
-    oogs_t* ogsFdm = elliptic->oogs.get();
-    const bool overlap = elliptic->overlap;
-    if (!overlap) {
-      if ((rc = fused_fdm_launch(mesh->Nq, 1, E, mesh->o_elementList.p, Su, o_Sx.p, o_Sy.p, o_Sz.p, o_invL.p,
-                                 elliptic->o_invDegreePfloat, o_work1.p, st)))
-        return rc;
-    } else if ((rc = fused_fdm_launch(mesh->Nq, 1, mesh->NglobalGatherElements, mesh->o_globalGatherElementList.p, Su,
-                                      o_Sx.p, o_Sy.p, o_Sz.p, o_invL.p, elliptic->o_invDegreePfloat, o_work1.p, st)))
+    if ((rc = fused_fdm_launch(mesh->Nq, 1, E, mesh->o_elementList.p, Su, o_Sx.p, o_Sy.p, o_Sz.p, o_invL.p,
+                               elliptic->o_invDegreePfloat, o_work1.p, st)))
       return rc;
-    if ((rc = ogsFdm->start<float>(Su, 1, 0, gs_op::add, st))) return rc;
-    if (overlap)
-      if ((rc = fused_fdm_launch(mesh->Nq, 1, mesh->NlocalGatherElements, mesh->o_localGatherElementList.p, Su, o_Sx.p,
-                                 o_Sy.p, o_Sz.p, o_invL.p, elliptic->o_invDegreePfloat, o_work1.p, st)))
-        return rc;
-    // finish + ellipticApplyMask in one launch (masked nodes belong to no row of the masked handle)
-    if (ogsFdm->ogs->NhaloGather) {
-      if ((rc = ogsFdm->finish<float>(Su, 1, 0, gs_op::add, 0, nullptr, st))) return rc;
-      return ellipticApplyMask<float>(elliptic, Su);
-    }
-    return ogsFdm->finish<float>(Su, 1, 0, gs_op::add, elliptic->Nmasked, elliptic->o_maskIds.p, st);
+    return elliptic->oogs->startFinish<float>(Su, 1, 0, gs_op::add, elliptic->Nmasked, elliptic->o_maskIds.p, st);
   }
   // ASM
   if ((rc = fused_fdm_launch(mesh->Nq, 0, E, mesh->o_elementList.p, o_work2.p, o_Sx.p, o_Sy.p, o_Sz.p, o_invL.p,
@@ -258,10 +242,6 @@ int pMGLevel::smoothSchwarz(const float* u, float* Su, bool /*xIsZero*/)
     return rc;
   if ((rc = ogsExt->startFinish<float>(o_work2.p, 1, 0, gs_op::add, 0, nullptr, st))) return rc;
   if ((rc = post_fdm_launch(mesh->Nq, E, o_work1.p, o_work2.p, Su, o_wts.p, st))) return rc;
-  if (elliptic->oogs->ogs->NhaloGather) {
-    if ((rc = elliptic->oogs->startFinish<float>(Su, 1, 0, gs_op::add, 0, nullptr, st))) return rc;
-    return ellipticApplyMask<float>(elliptic, Su);
-  }
   return elliptic->oogs->startFinish<float>(Su, 1, 0, gs_op::add, elliptic->Nmasked, elliptic->o_maskIds.p, st);
 }
 

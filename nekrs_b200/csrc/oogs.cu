@@ -228,11 +228,28 @@ int oogs_t::setup(ogs_t* ogs_, comm_t* comm_, int maxFields_)
   ogs = ogs_;
   comm = comm_;
   maxFields = std::max(1, maxFields_);
-  if (ogs->NhaloGather == 0 || !comm || comm->nranks == 1) {
+  if (!comm || comm->nranks == 1) {
     if (ogs->NhaloGather) {
       set_last_error("ogs has halo rows but no communicator was given");
       return NRSB_ERR_INVALID;
     }
+    return NRSB_OK;
+  }
+  if (ogs->NhaloGather == 0) {
+    // A rank without halo rows in THIS handle (all its interface nodes Dirichlet-masked, a coarse level that lives on
+    // fewer ranks, ...) still has to take part in the setup collectives of the ranks that have some: same sequence
+    // as below with empty contributions (counts, a dummy IPC handle nobody opens, the two barriers).
+    const int nr = comm->nranks;
+    std::vector<int> C0((size_t)nr * nr, 0);
+    comm->allgather_bytes(C0.data(), sizeof(int) * nr);
+    void* dummy = nullptr;
+    NRSB_CUDA(cudaMalloc(&dummy, 256));
+    std::vector<cudaIpcMemHandle_t> h0(nr);
+    NRSB_CUDA(cudaIpcGetMemHandle(&h0[comm->rank], dummy));
+    comm->allgather_bytes(h0.data(), sizeof(cudaIpcMemHandle_t));
+    comm->barrier();
+    comm->barrier();
+    cudaFree(dummy);
     return NRSB_OK;
   }
   const int nranks = comm->nranks, rank = comm->rank;

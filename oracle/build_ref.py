@@ -90,6 +90,14 @@ def ref_ax(N: int, prec: str = "d", poisson: bool = True, fast: bool = False) ->
     return _compile(name, ["elliptic/ellipticPartialAxCoeffHex3D.c"], d, fast)
 
 
+def ref_ax_block(N: int, lambda_field: int) -> str:
+    """ellipticBlockPartialAxCoeffHex3D_v0 (three fields, Helmholtz; p_lambda selects per-node coefficients)."""
+    Nq = N + 1
+    d = _common_defs(Nq)
+    d.update({"dfloat": "double", "pfloat": "float", "p_knl": 0, "p_lambda": lambda_field, "p_Nfields": 3})
+    return _compile("axblock_d_N%d_lambda%d" % (N, lambda_field), ["elliptic/ellipticBlockPartialAxCoeffHex3D.c"], d)
+
+
 def ref_fdm(N: int, restrict: int, fast: bool = False) -> str:
     Nq = N + 1
     d = _common_defs(Nq)
@@ -131,6 +139,9 @@ def build_ref(fast: bool = True) -> bool:
         ref_ax(N, "d")
         ref_ax(N, "f")
     ref_ax(7, "d", poisson=False)
+    for N in (3, 7):
+        ref_ax_block(N, 0)
+        ref_ax_block(N, 1)
     for N in FDM_ORDERS:
         ref_fdm(N, 1)
         ref_fdm(N, 0)

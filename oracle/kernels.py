@@ -66,6 +66,21 @@ class Orc:
            c_int(Nq), c_int(1 if poisson else 0), c_int(0))
         return Aq
 
+    def ax_block(self, N, element_list, ggeo, D, q, Aq, lambda0, lambda1, offset, loffset, lambda_field=False,
+                 Nfields=3):
+        """ellipticBlockPartialAxCoeffHex3D.c:2-152: the scalar Helmholtz operator field by field (q, Aq `offset`
+        apart, coefficients `loffset` apart); the per-node arithmetic of the reference's block kernel is the scalar
+        kernel's, statement for statement."""
+        Nq = N + 1
+        dt = q.dtype
+        S = np.ascontiguousarray(D.T)
+        fn = getattr(self.lib, "orc_ax_" + self._suf(q))
+        for f in range(Nfields):
+            fn(c_int(len(element_list)), c_int(0), c_int(0), _p(_chk(element_list, np.int32)), _p(_chk(ggeo, dt)),
+               _p(_chk(D, dt)), _p(S), _p(lambda0[f * loffset:]), _p(lambda1[f * loffset:]),
+               _p(q[f * offset:]), _p(Aq[f * offset:]), c_int(Nq), c_int(0), c_int(1 if lambda_field else 0))
+        return Aq
+
     def mask(self, mask_ids, q):
         getattr(self.lib, "orc_mask_" + self._suf(q))(c_int(len(mask_ids)), _p(_chk(mask_ids, np.int32)), _p(q))
 
@@ -185,6 +200,19 @@ class RefAx:
         lam1 = np.zeros(1, dtype=dt) if lambda1 is None else lambda1
         self.lib.ellipticPartialAxCoeffHex3D_v0(_r(len(element_list)), _r(0), _r(0), _p(element_list), _p(ggeo),
                                                 _p(D), _p(S), _p(lam0), _p(lam1), _p(q), _p(Aq))
+        return Aq
+
+
+class RefAxBlock:
+    """ellipticBlockPartialAxCoeffHex3D_v0 compiled from the reference (three fields)."""
+
+    def __init__(self, N, lambda_field):
+        self.lib = _ref("axblock_d_N%d_lambda%d" % (N, 1 if lambda_field else 0))
+
+    def __call__(self, element_list, ggeo, D, q, Aq, lambda0, lambda1, offset, loffset):
+        S = np.ascontiguousarray(D.T)
+        self.lib.ellipticBlockPartialAxCoeffHex3D_v0(_r(len(element_list)), _r(offset), _r(loffset), _p(element_list),
+                                                     _p(ggeo), _p(D), _p(S), _p(lambda0), _p(lambda1), _p(q), _p(Aq))
         return Aq
 
 

@@ -425,3 +425,34 @@ def test_linalg_many_family(dt):
     d = DB.zeros(Nf * off, dt)
     ops.linalg_many("axpbyzMany", prec, N, Nf, off, 2.0, DB(like=x), -3.0, DB(like=y), d)
     assert relerr(fields(d.download(dt)), dt(2) * fields(x) + dt(-3) * fields(y)) < tol
+
+
+@pytest.mark.parametrize("N", [3, 7, 9])
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("lambda_field", [False, True])
+def test_block_axhelm(orc, N, dt, lambda_field):
+    """ellipticBlockPartialAxCoeffHex3D: three fields sharing the geometric factors, per-field coefficients."""
+    E, Np = 19, (N + 1) ** 3
+    r = rng(60 + N)
+    g, _ = sem.jacobi_gll(N)
+    D = sem.dmatrix_1d(g).astype(dt)
+    ggeo = r.random((E, 7, Np)).astype(dt)
+    offset, loffset = E * Np + 24, E * Np + 8
+    q = r.random(3 * offset).astype(dt)
+    if lambda_field:
+        lam0, lam1 = (r.random(3 * loffset) + 0.5).astype(dt), r.random(3 * loffset).astype(dt)
+    else:
+        lam0, lam1 = np.zeros(3 * loffset, dt), np.zeros(3 * loffset, dt)
+        lam0[[0, loffset, 2 * loffset]] = [1.1, 1.2, 1.3]
+        lam1[[0, loffset, 2 * loffset]] = [0.5, 0.6, 0.7]
+    el = r.permutation(E)[: E - 3].astype(np.int32)
+    ref = np.full(3 * offset, -3.0, dtype=dt)
+    orc.ax_block(N, el, ggeo, D, q, ref, lam0, lam1, offset, loffset, lambda_field=lambda_field)
+    d_Aq = DB(like=np.full(3 * offset, -3.0, dtype=dt))
+    ops.ellipticBlockPartialAxCoeffHex3D(N, el.size, offset, loffset, DB(like=el), DB(like=ggeo), D, DB(like=lam0),
+                                         DB(like=lam1), DB(like=q), d_Aq, lambda_field=lambda_field, dtype=dt)
+    out = d_Aq.download(dt)
+    assert relerr(out, ref) < TOL[dt] * (10 if dt == np.float32 else 1)
+    untouched = np.setdiff1d(np.arange(E), el)
+    for f in range(3):
+        assert np.all(out[f * offset:f * offset + E * Np].reshape(E, Np)[untouched] == -3.0)

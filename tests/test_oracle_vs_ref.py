@@ -171,3 +171,33 @@ def test_krylov_helpers_bit_exact(orc):
     ref.copy_f2d(f1, d1)
     orc.copy_f2d(f2, d2)
     assert np.array_equal(d1, d2)
+
+
+@pytest.mark.parametrize("N", [3, 7])
+@pytest.mark.parametrize("lambda_field", [False, True])
+def test_block_ax_oracle_equals_reference_bit_exact(orc, N, lambda_field):
+    """The three-field Helmholtz operator (ellipticBlockPartialAxCoeffHex3D.c): the oracle applies its scalar restatement
+    field by field; bit-identical to the reference's block kernel compiled in place."""
+    from oracle import kernels as K
+    name = "axblock_d_N%d_lambda%d" % (N, 1 if lambda_field else 0)
+    if not K.ref_available(name):
+        pytest.skip("reference kernels not built here")
+    E, Np = 7, (N + 1) ** 3
+    r = np.random.Generator(np.random.PCG64(40 + N))
+    g, _ = sem.jacobi_gll(N)
+    D = sem.dmatrix_1d(g)
+    ggeo = r.random((E, 7, Np))
+    offset, loffset = E * Np + 16, E * Np + 8
+    q = r.random(3 * offset)
+    if lambda_field:
+        lam0, lam1 = r.random(3 * loffset) + 0.5, r.random(3 * loffset)
+    else:
+        lam0, lam1 = np.zeros(3 * loffset), np.zeros(3 * loffset)
+        lam0[[0, loffset, 2 * loffset]] = [1.1, 1.2, 1.3]
+        lam1[[0, loffset, 2 * loffset]] = [0.5, 0.6, 0.7]
+    el = r.permutation(E).astype(np.int32)[:5]
+    a = np.full(3 * offset, -2.0)
+    b = a.copy()
+    orc.ax_block(N, el, ggeo, D, q, a, lam0, lam1, offset, loffset, lambda_field=lambda_field)
+    K.RefAxBlock(N, lambda_field)(el, ggeo, D, q, b, lam0, lam1, offset, loffset)
+    assert np.array_equal(a, b)
