@@ -36,13 +36,21 @@ bool pdl_enabled(bool producer)
   return producer ? ax : gs;
 }
 
-int ax_default_variant(int Nq, int precision)
+bool ax_tma_nq_supported(int Nq, int precision);  // axhelm_tma_nq.cu
+
+int ax_default_pencil_variant(int Nq, int precision)
 {
-  if (Nq == 8) return 5;  // persistent TMA-ring kernel (axhelm_tma.cu)
   // measured (profiles/r1_sweep_ax_N3to9_v2.json, E=4096): in fp64 the >= 512-threads-per-SM build of the pencil
   // kernel (variant 2) spills at Nq = 7 and Nq >= 9 (N=9: 156 us against 88 us for variant 1)
   if (precision == 8 && (Nq == 7 || Nq >= 9)) return 1;
   return Nq >= 3 ? 2 : 0;
+}
+
+int ax_default_variant(int Nq, int precision)
+{
+  if (Nq == 8) return 5;  // persistent TMA-ring kernel (axhelm_tma.cu)
+  if (ax_tma_nq_supported(Nq, precision)) return 4;  // the same kernel for the other even Nq where it wins
+  return ax_default_pencil_variant(Nq, precision);
 }
 
 // process-wide scratch for the kernel-level reductions that return a value to the host

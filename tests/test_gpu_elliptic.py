@@ -435,9 +435,12 @@ def test_solution_projection(orc):
         x = np.zeros(n)
         it = ell.solve_host(rhs, x)
         iters.append((it, ref.Niter))
-        # the projection basis is built from previous (tolerance-level different) solutions: +-2
-        assert abs(it - ref.Niter) <= 2, iters
-        assert relerr(x, x_ref) < 1e-6
+        # unprojected solves (step 0, 1): same count.  Later the residual left by the projection is at round-off level
+        # relative to the right-hand side, so the last iterations creep along the tolerance and the count depends on
+        # the last bits of Ax (measured: 55 or 57 against the oracle's 53 for two axhelm kernels whose solutions
+        # both agree with the oracle's to 1.2e-15)
+        assert abs(it - ref.Niter) <= (1 if step < 2 else 4), iters
+        assert relerr(x, x_ref) < 1e-12
     assert ell.res00Norm > ell.res0Norm          # the projection removed part of the residual
 
 

@@ -83,6 +83,35 @@ def test_axhelm_helmholtz(orc, variant, lambda_field):
     assert relerr(d_Aq.download(), ref) < 1e-12
 
 
+@pytest.mark.parametrize("N,dt", [(5, np.float64), (9, np.float64), (9, np.float32), (11, np.float32)])
+@pytest.mark.parametrize("poisson", [True, False])
+def test_axhelm_tma_ring_other_orders(orc, N, dt, poisson):
+    """The persistent TMA-ring kernel at the even Nq other than 8 (axhelm_tma_nq.cu; padded consumer groups): more
+    elements than one round of the ring per group, a permuted element list, and the default dispatch (-1) must pick
+    the same kernel as variant 4 (bit-identical output)."""
+    E, Np = 1500, (N + 1) ** 3
+    r = rng(300 + N)
+    g, _ = sem.jacobi_gll(N)
+    D = sem.dmatrix_1d(g).astype(dt)
+    ggeo = r.random((E, 7, Np)).astype(dt)
+    q = r.random(E * Np).astype(dt)
+    el = r.permutation(E)[: E - 7].astype(np.int32)
+    lam0, lam1 = np.full(1, 1.3, dtype=dt), np.full(1, 0.7, dtype=dt)
+    ref = np.full(E * Np, -3.0, dtype=dt)
+    orc.ax(N, el, ggeo, D, q, ref, lambda0=lam0, lambda1=lam1, poisson=poisson)
+    outs = []
+    for variant in (4, -1):
+        d_Aq = DB(like=np.full(E * Np, -3.0, dtype=dt))
+        ops.ellipticPartialAxCoeffHex3D(N, DB(like=el), DB(like=ggeo), D, DB(like=q), d_Aq, Nelements=el.size,
+                                        lambda0=DB(like=lam0), lambda1=DB(like=lam1), poisson=poisson,
+                                        variant=variant, dtype=dt)
+        outs.append(d_Aq.download(dt))
+    assert relerr(outs[0], ref) < TOL[dt] * (10 if dt == np.float32 else 1)
+    assert np.array_equal(outs[0], outs[1])
+    untouched = np.setdiff1d(np.arange(E), el)
+    assert np.all(outs[0].reshape(E, Np)[untouched] == -3.0)
+
+
 def test_axhelm_empty_list():
     D = np.eye(8)
     ops.ellipticPartialAxCoeffHex3D(7, DB(like=np.zeros(1, np.int32)), None, D, None, None, Nelements=0,
