@@ -263,9 +263,12 @@ static int fused_launch(int restrict_, dlong Nelements, const dlong* elementList
 
 int fused_fdm_v1_launch(int Nq, int restrict_, dlong Nelements, const dlong* elementList, float* Su, const float* Sx,
                         const float* Sy, const float* Sz, const float* invL, const float* wts, float* u,
-                        cudaStream_t stream, int epb);
+                        cudaStream_t stream, int epb, int warp);
 bool fdm_supported(int Nq) { return Nq + 2 >= 4 && Nq + 2 <= 14; }
-static int g_fdm_variant = 1;  // 0: one pencil per thread (this file); 1: register-blocked pairs (fdm_v1.cu)
+// 0: one pencil per thread (this file); 1: four pencils per thread (fdm_v1.cu), several elements per block;
+// 2: the same with one element per warp where an element has <= 32 pencil owners (Nq = 8);  1x / 2x: developer
+// override of the elements (warps) per block
+static int g_fdm_variant = 2;
 void set_fdm_variant(int v) { g_fdm_variant = v; }
 
 int fused_fdm_launch(int Nq, int restrict_, dlong Nelements, const dlong* elementList, float* Su, const float* Sx,
@@ -274,8 +277,10 @@ int fused_fdm_launch(int Nq, int restrict_, dlong Nelements, const dlong* elemen
 {
   if (Nelements == 0) return NRSB_OK;
   if (g_fdm_variant >= 1) {
+    const int warp = g_fdm_variant == 2 || g_fdm_variant >= 20;
+    const int epb = g_fdm_variant >= 20 ? g_fdm_variant - 20 : (g_fdm_variant >= 10 ? g_fdm_variant - 10 : 0);
     const int rc = fused_fdm_v1_launch(Nq, restrict_, Nelements, elementList, Su, Sx, Sy, Sz, invL, wts, u, stream,
-                                       g_fdm_variant >= 10 ? g_fdm_variant - 10 : 0);
+                                       epb, warp);
     if (rc != 1) return rc;  // 1 = size not covered (odd extended size): fall through to variant 0
   }
 #define CALL(n) return fused_launch<n>(restrict_, Nelements, elementList, Su, Sx, Sy, Sz, invL, wts, u, stream);

@@ -29,17 +29,29 @@ struct FdmV1 {
   static constexpr int smemFloats = 2 * Npe + 6 * Nqe * SP;
 };
 
+// two fp32 FMAs in one issue slot (Blackwell FFMA2; each half is an ordinary fma.rn, so the results are those of the
+// scalar code).  The kernel is issue-bound (ncu: 58 % of the issue slots busy at 4 warps per scheduler, 70 % of the
+// instructions FFMA): pairing the FMAs removes 35 % of the instructions.
+__device__ __forceinline__ void ffma2(float2& acc, const float2 a, const float2 b)
+{
+  unsigned long long& c = reinterpret_cast<unsigned long long&>(acc);
+  asm("fma.rn.f32x2 %0, %1, %2, %0;"
+      : "+l"(c)
+      : "l"(reinterpret_cast<const unsigned long long&>(a)), "l"(reinterpret_cast<const unsigned long long&>(b)));
+}
+
 // one contraction pass: out[o][row] = (scale) * sum_l S[l][o] in[row][l]   for the thread's PPT rows
 template <int Nqe, bool kScale>
 __device__ __forceinline__ void fdm_pass(const float* __restrict__ S, const float* in, float* out, int t,
                                          const float (&scale)[FdmV1<Nqe>::PPT][Nqe])
 {
   using F = FdmV1<Nqe>;
-  float acc[F::PPT][Nqe];
+  static_assert(Nqe % 2 == 0, "outputs are accumulated in pairs");
+  float2 acc[F::PPT][Nqe / 2];
 #pragma unroll
   for (int q = 0; q < F::PPT; ++q)
 #pragma unroll
-    for (int o = 0; o < Nqe; ++o) acc[q][o] = 0.f;
+    for (int o = 0; o < Nqe / 2; ++o) acc[q][o] = make_float2(0.f, 0.f);
 #pragma unroll
   for (int l = 0; l < Nqe; l += 2) {
     float2 v[F::PPT];
@@ -47,20 +59,19 @@ __device__ __forceinline__ void fdm_pass(const float* __restrict__ S, const floa
     for (int q = 0; q < F::PPT; ++q) v[q] = *reinterpret_cast<const float2*>(in + (t + F::TPE * q) * Nqe + l);
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      float s[F::SP];
+      float2 s[F::SP / 2];
 #pragma unroll
       for (int c = 0; c < F::SP / 4; ++c) {
         const float4 w = *reinterpret_cast<const float4*>(S + (l + h) * F::SP + 4 * c);
-        s[4 * c + 0] = w.x;
-        s[4 * c + 1] = w.y;
-        s[4 * c + 2] = w.z;
-        s[4 * c + 3] = w.w;
+        s[2 * c + 0] = make_float2(w.x, w.y);
+        s[2 * c + 1] = make_float2(w.z, w.w);
       }
 #pragma unroll
       for (int q = 0; q < F::PPT; ++q) {
         const float x = h ? v[q].y : v[q].x;
+        const float2 xx = make_float2(x, x);
 #pragma unroll
-        for (int o = 0; o < Nqe; ++o) acc[q][o] += s[o] * x;
+        for (int o = 0; o < Nqe / 2; ++o) ffma2(acc[q][o], s[o], xx);
       }
     }
   }
@@ -68,14 +79,19 @@ __device__ __forceinline__ void fdm_pass(const float* __restrict__ S, const floa
   for (int o = 0; o < Nqe; ++o)
 #pragma unroll
     for (int q = 0; q < F::PPT; ++q) {
-      float r = acc[q][o];
+      float r = (o & 1) ? acc[q][o / 2].y : acc[q][o / 2].x;
       if (kScale) r *= scale[q][o];
       out[o * F::Nrows + t + F::TPE * q] = r;
     }
 }
 
-template <int Nqe, bool kRestrict, int EPB>
-__global__ void __launch_bounds__(FdmV1<Nqe>::TPE* EPB)
+// kWarp (TPE <= 32): one element per WARP (lanes >= TPE idle).  The element's slabs are then private to the warp:
+// no lane of another element shares a wavefront with it (the 10 880-byte slabs of Nqe = 10 all start on bank 0, and
+// with 25 threads per element every warp straddled two of them: 39 % of the shared-memory wavefronts were conflicts,
+// profiles/r2_ncu_fused_fdm_v1_E4096.md), the seven block barriers become __syncwarp, and the warps of a block drift
+// apart so that one warp's global loads overlap another's contraction passes.
+template <int Nqe, bool kRestrict, int EPB, bool kWarp>
+__global__ void __launch_bounds__((kWarp ? 32 : FdmV1<Nqe>::TPE) * EPB, (kWarp && EPB <= 16) ? 16 / EPB : 1)
     fused_fdm_v1_kernel(const dlong Nelements, const dlong* __restrict__ elementList, float* __restrict__ Su,
                         const float* __restrict__ S_x, const float* __restrict__ S_y, const float* __restrict__ S_z,
                         const float* __restrict__ inv_L, const float* __restrict__ wts, float* __restrict__ u)
@@ -86,11 +102,19 @@ __global__ void __launch_bounds__(FdmV1<Nqe>::TPE* EPB)
   constexpr int Npe = F::Npe;
   extern __shared__ __align__(16) float smem[];
   const int tid = threadIdx.x;
-  const int t = tid % F::TPE;
-  const int es = tid / F::TPE;
+  constexpr int TPB = kWarp ? 32 : F::TPE;  // threads per element slot of the block
+  const int t = tid % TPB;
+  const int es = tid / TPB;
   const dlong e = blockIdx.x * EPB + es;
-  const bool active = e < Nelements;
+  const bool lane = !kWarp || t < F::TPE;  // this thread owns pencils
+  const bool active = e < Nelements && lane;
   const dlong element = active ? elementList[e] : 0;
+  auto sync = [] {
+    if constexpr (kWarp)
+      __syncwarp();
+    else
+      __syncthreads();
+  };
   float* A = smem + (size_t)es * F::smemFloats;
   float* B = A + Npe;
   float* Sxf = B + Npe;  // forward  (row l: S[l][o])
@@ -134,12 +158,12 @@ __global__ void __launch_bounds__(FdmV1<Nqe>::TPE* EPB)
 #pragma unroll
     for (int n = 0; n < NU; ++n) {
       const int idx = t + n * F::TPE;
-      if (idx < Npe / 4) dst[idx] = ru[n];
+      if (lane && idx < Npe / 4) dst[idx] = ru[n];
     }
 #pragma unroll
     for (int n = 0; n < NS; ++n) {
       const int idx = t + n * F::TPE;
-      if (idx < Nqe2) {
+      if (lane && idx < Nqe2) {
         const int l = idx / Nqe, o = idx - l * Nqe;
         Sxf[l * F::SP + o] = rs[0][n];
         Syf[l * F::SP + o] = rs[1][n];
@@ -150,11 +174,11 @@ __global__ void __launch_bounds__(FdmV1<Nqe>::TPE* EPB)
       }
     }
   }
-  __syncthreads();
+  sync();
 
   // ---- subtract the element's own contribution from the overlap planes (fusedFDM.c:33-92)
 #define AI(k, j, i) (((k)*Nqe + (j)) * Nqe + (i))
-  for (int idx = t; idx < Nq * Nq; idx += F::TPE) {
+  for (int idx = lane ? t : Nq * Nq; idx < Nq * Nq; idx += F::TPE) {
     const int a = 1 + idx % Nq, b = 1 + idx / Nq;
     A[AI(0, b, a)] -= A[AI(2, b, a)];
     A[AI(Nqe - 1, b, a)] -= A[AI(Nqe - 3, b, a)];
@@ -163,20 +187,20 @@ __global__ void __launch_bounds__(FdmV1<Nqe>::TPE* EPB)
     A[AI(b, a, 0)] -= A[AI(b, a, 2)];
     A[AI(b, a, Nqe - 1)] -= A[AI(b, a, Nqe - 3)];
   }
-  __syncthreads();
+  sync();
 
   // forward: S^T in x, y, z (each pass rotates the layout; three passes restore [z][y][x]), then scale
-  fdm_pass<Nqe, false>(Sxf, A, B, t, il);
-  __syncthreads();
-  fdm_pass<Nqe, false>(Syf, B, A, t, il);
-  __syncthreads();
-  fdm_pass<Nqe, true>(Szf, A, B, t, il);
-  __syncthreads();
+  if (lane) fdm_pass<Nqe, false>(Sxf, A, B, t, il);
+  sync();
+  if (lane) fdm_pass<Nqe, false>(Syf, B, A, t, il);
+  sync();
+  if (lane) fdm_pass<Nqe, true>(Szf, A, B, t, il);
+  sync();
   // backward: S in x, y, z
-  fdm_pass<Nqe, false>(Sxt, B, A, t, il);
-  __syncthreads();
-  fdm_pass<Nqe, false>(Syt, A, B, t, il);
-  __syncthreads();
+  if (lane) fdm_pass<Nqe, false>(Sxt, B, A, t, il);
+  sync();
+  if (lane) fdm_pass<Nqe, false>(Syt, A, B, t, il);
+  sync();
   // RAS weights of this thread's outputs: issued before the last pass so the latency hides behind it
   constexpr int NW = (Nq * Nq * Nq + F::TPE - 1) / F::TPE;
   float rw[kRestrict ? NW : 1];
@@ -188,8 +212,8 @@ __global__ void __launch_bounds__(FdmV1<Nqe>::TPE* EPB)
       rw[n] = (active && idx < Nq * Nq * Nq) ? __ldg(wts + base + idx) : 0.f;
     }
   }
-  fdm_pass<Nqe, false>(Szt, B, A, t, il);
-  __syncthreads();
+  if (lane) fdm_pass<Nqe, false>(Szt, B, A, t, il);
+  sync();
 
   if (!active) return;
   if (kRestrict) {
@@ -217,30 +241,32 @@ __global__ void __launch_bounds__(FdmV1<Nqe>::TPE* EPB)
 #undef AI
 }
 
-template <int Nqe, int EPBO = 0>
+template <int Nqe, int EPBO = 0, bool kWarp = false>
 int launch_v1(int restrict_, dlong Nelements, const dlong* elementList, float* Su, const float* Sx, const float* Sy,
               const float* Sz, const float* invL, const float* wts, float* u, cudaStream_t stream)
 {
   using F = FdmV1<Nqe>;
+  static_assert(!kWarp || F::TPE <= 32, "one element per warp needs at most 32 pencil owners");
   constexpr int want = (192 + F::TPE - 1) / F::TPE;
   constexpr int EPB = EPBO ? EPBO : (want > 32 ? 32 : (want < 1 ? 1 : want));
+  constexpr int TPB = kWarp ? 32 : F::TPE;
   const size_t smem = (size_t)EPB * F::smemFloats * sizeof(float);
   const int grid = (Nelements + EPB - 1) / EPB;
   static bool configured[2] = {false, false};
   if (restrict_) {
-    auto k = fused_fdm_v1_kernel<Nqe, true, EPB>;
+    auto k = fused_fdm_v1_kernel<Nqe, true, EPB, kWarp>;
     if (!configured[1]) {
       NRSB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       configured[1] = true;
     }
-    k<<<grid, F::TPE * EPB, smem, stream>>>(Nelements, elementList, Su, Sx, Sy, Sz, invL, wts, u);
+    k<<<grid, TPB * EPB, smem, stream>>>(Nelements, elementList, Su, Sx, Sy, Sz, invL, wts, u);
   } else {
-    auto k = fused_fdm_v1_kernel<Nqe, false, EPB>;
+    auto k = fused_fdm_v1_kernel<Nqe, false, EPB, kWarp>;
     if (!configured[0]) {
       NRSB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       configured[0] = true;
     }
-    k<<<grid, F::TPE * EPB, smem, stream>>>(Nelements, elementList, Su, Sx, Sy, Sz, invL, wts, u);
+    k<<<grid, TPB * EPB, smem, stream>>>(Nelements, elementList, Su, Sx, Sy, Sz, invL, wts, u);
   }
   NRSB_CHECK_LAUNCH();
   return NRSB_OK;
@@ -248,29 +274,38 @@ int launch_v1(int restrict_, dlong Nelements, const dlong* elementList, float* S
 
 }  // namespace
 
-// returns 1 if this size is not handled here (odd Nqe)
+// returns 1 if this size is not handled here (odd Nqe).  epb > 0: developer override of the elements per block;
+// warp: one element per warp (Nqe = 10: the default; epb = warps per block)
 int fused_fdm_v1_launch(int Nq, int restrict_, dlong Nelements, const dlong* elementList, float* Su, const float* Sx,
                         const float* Sy, const float* Sz, const float* invL, const float* wts, float* u,
-                        cudaStream_t stream, int epb)
+                        cudaStream_t stream, int epb, int warp)
 {
-  if (Nq == 8) {
+#define ARGS restrict_, Nelements, elementList, Su, Sx, Sy, Sz, invL, wts, u, stream
+  if (Nq == 8 && warp) {
     switch (epb) {
-      case 1: return launch_v1<10, 1>(restrict_, Nelements, elementList, Su, Sx, Sy, Sz, invL, wts, u, stream);
-      case 2: return launch_v1<10, 2>(restrict_, Nelements, elementList, Su, Sx, Sy, Sz, invL, wts, u, stream);
-      case 3: return launch_v1<10, 3>(restrict_, Nelements, elementList, Su, Sx, Sy, Sz, invL, wts, u, stream);
-      case 4: return launch_v1<10, 4>(restrict_, Nelements, elementList, Su, Sx, Sy, Sz, invL, wts, u, stream);
-      case 5: return launch_v1<10, 5>(restrict_, Nelements, elementList, Su, Sx, Sy, Sz, invL, wts, u, stream);
+      case 1: return launch_v1<10, 1, true>(ARGS);
+      case 2: return launch_v1<10, 2, true>(ARGS);
+      case 6: return launch_v1<10, 6, true>(ARGS);
+      case 8: return launch_v1<10, 8, true>(ARGS);
+      default: return launch_v1<10, 4, true>(ARGS);
+    }
+  }
+  if (Nq == 8 && epb) {
+    switch (epb) {
+      case 2: return launch_v1<10, 2>(ARGS);
+      case 4: return launch_v1<10, 4>(ARGS);
       default: break;
     }
   }
   switch (Nq + 2) {
-    case 4: return launch_v1<4>(restrict_, Nelements, elementList, Su, Sx, Sy, Sz, invL, wts, u, stream);
-    case 6: return launch_v1<6>(restrict_, Nelements, elementList, Su, Sx, Sy, Sz, invL, wts, u, stream);
-    case 8: return launch_v1<8>(restrict_, Nelements, elementList, Su, Sx, Sy, Sz, invL, wts, u, stream);
-    case 10: return launch_v1<10>(restrict_, Nelements, elementList, Su, Sx, Sy, Sz, invL, wts, u, stream);
-    case 12: return launch_v1<12>(restrict_, Nelements, elementList, Su, Sx, Sy, Sz, invL, wts, u, stream);
+    case 4: return launch_v1<4>(ARGS);
+    case 6: return launch_v1<6>(ARGS);
+    case 8: return launch_v1<8>(ARGS);
+    case 10: return launch_v1<10>(ARGS);
+    case 12: return launch_v1<12>(ARGS);
     default: return 1;
   }
+#undef ARGS
 }
 
 }  // namespace nrsb

@@ -300,7 +300,7 @@ def test_chebyshev_updates(orc):
 # ------------------------------------------------------------------------------------ FDM / transfers
 @pytest.mark.parametrize("N", [1, 2, 3, 5, 7, 9])
 @pytest.mark.parametrize("restrict", [1, 0])
-@pytest.mark.parametrize("fdm_variant", [0, 1])
+@pytest.mark.parametrize("fdm_variant", [0, 1, 2])
 def test_fdm(orc, N, restrict, fdm_variant):
     import ctypes
     lib.call("nrsb_set_fdm_variant", ctypes.c_int(fdm_variant))

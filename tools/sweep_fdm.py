@@ -66,7 +66,7 @@ def main():
             rec = dict(kernel="preFDM", N=N, E=E, ms=med, GBs=E * (Nq ** 3 + Nqe ** 3) * 4 / (med * 1e-3) / 1e9)
             res.append(rec)
             print(json.dumps(rec), flush=True)
-    lib.call("nrsb_set_fdm_variant", ctypes.c_int(1))
+    lib.call("nrsb_set_fdm_variant", ctypes.c_int(2))
     if args.out:
         json.dump(res, open(args.out, "w"), indent=1)
 
