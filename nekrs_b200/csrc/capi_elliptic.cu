@@ -474,6 +474,8 @@ int nrsb_elliptic_get_int(nrsb_elliptic_t h, const char* key, int64_t* value)
   else if (k == "NhaloGather") *value = e.ogs->NhaloGather;
   else if (k == "nLevels") *value = (e.precon && e.precon->MGSolver) ? (int64_t)e.precon->MGSolver->levels.size() : 0;
   else if (k == "coarseIterations") *value = (e.precon && e.precon->coarse) ? e.precon->coarse->iterations() : 0;
+  else if (k == "coarseGridSize") *value = (e.precon && e.precon->coarse) ? e.precon->coarse->gridSize : 0;
+  else if (k == "coarseClusterSize") *value = (e.precon && e.precon->coarse) ? e.precon->coarse->clusterSize : 0;
   else if (k == "axVariantFp64") *value = e.ax_variant[0];
   else if (k == "axVariantFp32") *value = e.ax_variant[1];
   else {

@@ -248,7 +248,8 @@ int coarseSolver_t::setup(pMGLevel* lvl, int maxIter_, double tol_)
   if ((rc = scal.alloc(C_COUNT))) return rc;
   if (multiRank && mesh->comm && mesh->comm->nranks > 1 && !e->options.compareArgs("COARSE SOLVER REPLICATED", "FALSE"))
     if ((rc = setup_replicated(idsT, rowNode, tIndex, rows))) return rc;
-  return plan_cluster();
+  if ((rc = plan_cluster())) return rc;
+  return plan_grid();
 }
 
 coarseSolver_t::~coarseSolver_t()
@@ -414,7 +415,12 @@ int coarseSolver_t::solve(float* rhs, float* xE)
   const int grid = (NT + kBlockSize - 1) / kBlockSize;
   double* S = scal.p;
   int rc;
-  if (variant >= 1 && clusterSize > 0 && (!multiRank || replicated)) return solve_cluster(rhs, xE);
+  if (variant >= 1 && (!multiRank || replicated)) {
+    const int n = replicated ? NTg : NT;
+    const bool preferGrid = variant == 3 || (variant == 1 && (n > kGridRows || clusterSize == 0));
+    if (gridSize > 0 && (preferGrid || clusterSize == 0) && variant != 2 && variant != 4) return solve_grid(rhs, xE);
+    if (clusterSize > 0) return solve_cluster(rhs, xE);
+  }
   iterOnDevice = false;
   lastIter = 0;
   if (NT > 0) {

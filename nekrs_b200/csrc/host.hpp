@@ -275,6 +275,12 @@ class coarseSolver_t {
   int clusterSize = 0, clusterRPC = 0, clusterRmax = 0, clusterMatInSmem = 0, clusterUGlobal = 0;
   size_t clusterSmem = 0;
   dbuf<float> uScratch;
+  // single-kernel grid path (coarse_grid.cu: all SMs, grid barrier); gridSize == 0 -> not available
+  int gridSize = 0, gridRPC = 0, gridRmax = 0, gridMatInSmem = 0;
+  size_t gridSmem = 0;
+  dbuf<float> gridU;
+  dbuf<double> gridRed;
+  dbuf<unsigned> gridBar;
   // several ranks: replicated global coarse problem for the cluster kernel (coarse_cluster.cu header)
   bool replicated = false;
   int NTg = 0, gEllWidth = 0, nOwn = 0;
@@ -288,12 +294,18 @@ class coarseSolver_t {
   int setup_replicated(const std::vector<hlong>& idsT, const std::vector<int>& rowNode,
                        const std::vector<int>& tIndex, const std::vector<std::map<int, double>>& rows);
   ~coarseSolver_t();
-  static int variant;  // 1 (default): cluster kernel when it fits; 0: always the multi-launch path
+  // 1 (default): one-kernel solve -- the grid kernel for large systems (> kGridRows rows or replicated), else the
+  // cluster kernel; 0: always the multi-launch path; 2: cluster kernel with the SpMV input through L2 (tests);
+  // 3: grid kernel whenever it is available; 4: cluster kernel whenever it is available
+  static int variant;
+  static constexpr int kGridRows = 16384;
   int setup(pMGLevel* lvl, int maxIter, double tol);
   int solve(float* rhs, float* x);
   int spmv_dots(bool first);
   int plan_cluster();
   int solve_cluster(float* rhs, float* x);
+  int plan_grid();
+  int solve_grid(float* rhs, float* x);
   int iterations();
 };
 

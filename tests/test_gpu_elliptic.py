@@ -491,15 +491,20 @@ def test_coarse_cluster_kernel_matches_multilaunch_and_oracle(orc, nel):
     rhs[Lc.ell.mask_ids] = 0
     out = {}
     try:
-        for variant in (1, 0):
+        for variant in (4, 0, 3):   # cluster kernel, multi-launch path, grid kernel (coarse_grid.cu)
             _lib.call("nrsb_set_coarse_variant", ctypes.c_int(variant))
             d_x = DB.zeros(n1, np.float32)
-            ell.level_op(k, "coarseSolve", DB(like=rhs), d_x)
+            for rep in range(3):    # the grid kernel's barrier counter and parity buffers across launches
+                ell.level_op(k, "coarseSolve", DB(like=rhs), d_x)
             out[variant] = (d_x.download(), ell.get_int("coarseIterations"))
     finally:
         _lib.call("nrsb_set_coarse_variant", ctypes.c_int(1))
+    assert ell.get_int("coarseGridSize") > 0 and ell.get_int("coarseClusterSize") > 0
+    out[1] = out[4]
     assert out[1][1] == out[0][1] and out[1][1] > 0
     assert relerr(out[1][0], out[0][0]) < 2e-5
+    assert out[3][1] == out[0][1]
+    assert relerr(out[3][0], out[0][0]) < 2e-5
     d_x = DB.zeros(n1, np.float32)
     ell_l2.level_op(k, "coarseSolve", DB(like=rhs), d_x)
     assert ell_l2.get_int("coarseIterations") == out[1][1]
@@ -511,8 +516,9 @@ def test_coarse_cluster_kernel_matches_multilaunch_and_oracle(orc, nel):
 
 
 def test_coarse_cluster_kernel_large_grid():
-    """68 921 coarse unknowns: 8 rows per thread, SpMV input through L2 (what the replicated coarse problem
-    of an 8-GPU job looks like).  Product-only check: cluster kernel == multi-launch path."""
+    """68 921 coarse unknowns (what the replicated coarse problem of an 8-GPU job looks like): the cluster kernel
+    (8 rows per thread, SpMV input through L2), the grid kernel on all SMs (the default at this size) and the
+    multi-launch path agree.  Product-only check."""
     import ctypes
     from nekrs_b200 import lib as _lib
     mesh = meshgen.box_mesh(3, (42, 42, 42), kershaw_eps=0.3)
@@ -523,12 +529,14 @@ def test_coarse_cluster_kernel_large_grid():
     rhs = np.random.Generator(np.random.PCG64(3)).random(n1).astype(np.float32) - 0.5
     out = {}
     try:
-        for variant in (1, 0):
+        for variant in (4, 0, 3, 1):   # cluster, multi-launch, grid kernel, default (= grid at this size)
             _lib.call("nrsb_set_coarse_variant", ctypes.c_int(variant))
             d_x = DB.zeros(n1, np.float32)
             ell.level_op(k, "coarseSolve", DB(like=rhs), d_x)
             out[variant] = (d_x.download(), ell.get_int("coarseIterations"))
     finally:
         _lib.call("nrsb_set_coarse_variant", ctypes.c_int(1))
-    assert out[1][1] == out[0][1] and out[1][1] > 0
-    assert relerr(out[1][0], out[0][0]) < 5e-5
+    assert out[4][1] == out[0][1] and out[4][1] > 0
+    assert relerr(out[4][0], out[0][0]) < 5e-5
+    assert out[3][1] == out[0][1] and relerr(out[3][0], out[0][0]) < 5e-5
+    assert np.array_equal(out[1][0], out[3][0])
