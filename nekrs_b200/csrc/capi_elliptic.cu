@@ -468,6 +468,7 @@ int nrsb_elliptic_get_int(nrsb_elliptic_t h, const char* key, int64_t* value)
   else if (k == "Nmasked") *value = e.Nmasked;
   else if (k == "Niter") *value = e.Niter;
   else if (k == "overlap") *value = e.overlap;
+  else if (k == "splitOverlap") *value = e.splitOverlap;
   else if (k == "allNeumann") *value = e.allNeumann;
   else if (k == "NglobalGatherElements") *value = e.mesh->NglobalGatherElements;
   else if (k == "NlocalGatherElements") *value = e.mesh->NlocalGatherElements;
@@ -509,6 +510,8 @@ int nrsb_elliptic_get_real(nrsb_elliptic_t h, const char* key, double* value)
   else if (k == "res0Norm") *value = e.res0Norm;
   else if (k == "res00Norm") *value = e.res00Norm;
   else if (k == "resNorm") *value = e.resNorm;
+  else if (k == "overlapTimeUnsplit") *value = e.overlapTimes[0];
+  else if (k == "overlapTimeSplit") *value = e.overlapTimes[1];
   else {
     set_last_error("unknown key " + k);
     return NRSB_ERR_INVALID;

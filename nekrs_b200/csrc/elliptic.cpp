@@ -295,7 +295,7 @@ int ellipticOperator(elliptic_t* elliptic, const T* o_q, T* o_Aq, bool masked, A
   // system-scope fence here) only pays when the exchange is slow.  With the one-launch flag-in-data exchange
   // (oogs_t::exchange_ll) the unsplit form below -- Ax on all elements, then ONE gather-scatter + exchange launch --
   // is faster on every multigrid level; ENABLE GS COMM OVERLAP = SPLIT keeps the reference's sequence.
-  if (elliptic->overlap && elliptic->options.compareArgs("ENABLE GS COMM OVERLAP", "SPLIT")) {
+  if (elliptic->overlap && elliptic->splitOverlap) {
     if ((rc = ellipticAx<T>(elliptic, mesh->NglobalGatherElements, mesh->o_globalGatherElementList.p, o_q, o_Aq)))
       return rc;
     if (masked && elliptic->NmaskedGlobal)
@@ -315,6 +315,76 @@ int ellipticOperator(elliptic_t* elliptic, const T* o_q, T* o_Aq, bool masked, A
 }
 template int ellipticOperator<double>(elliptic_t*, const double*, double*, bool, AxDot*);
 template int ellipticOperator<float>(elliptic_t*, const float*, float*, bool, AxDot*);
+
+// "testing Ax overlap" of ellipticSetup.cpp:255-302 (solver handle, fp64) and ellipticMultiGridSetup.cpp:123-150
+// (levels, fp32): one warm-up, barrier, 10 operator applications, the max over ranks decides -- so every rank takes
+// the same branch.  The default (TRUE) does not measure: the unsplit form with the one-launch exchange won on every
+// level and GPU count measured in round 2.
+template <typename T>
+static int time_operator(elliptic_t* elliptic, T* q, T* Aq, double* seconds)
+{
+  comm_t* comm = elliptic->mesh->comm;
+  const int Nsamples = 10;
+  int rc;
+  if ((rc = ellipticOperator<T>(elliptic, q, Aq, true, nullptr))) return rc;
+  NRSB_CUDA(cudaStreamSynchronize(elliptic->stream));
+  if (comm && comm->barrier) comm->barrier();
+  cudaEvent_t a, b;
+  NRSB_CUDA(cudaEventCreate(&a));
+  NRSB_CUDA(cudaEventCreate(&b));
+  NRSB_CUDA(cudaEventRecord(a, elliptic->stream));
+  for (int test = 0; test < Nsamples && !rc; ++test) rc = ellipticOperator<T>(elliptic, q, Aq, true, nullptr);
+  NRSB_CUDA(cudaEventRecord(b, elliptic->stream));
+  NRSB_CUDA(cudaEventSynchronize(b));
+  float ms = 0.f;
+  NRSB_CUDA(cudaEventElapsedTime(&ms, a, b));
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  if (rc) return rc;
+  double t = (double)ms * 1e-3 / Nsamples;
+  if (comm && comm->nranks > 1 && comm->allgather_bytes) {
+    std::vector<double> all(comm->nranks, 0.0);
+    all[comm->rank] = t;
+    comm->allgather_bytes(all.data(), sizeof(double));
+    for (double v : all) t = std::max(t, v);
+  }
+  *seconds = t;
+  return NRSB_OK;
+}
+
+int ellipticChooseOverlap(elliptic_t* elliptic, int precision)
+{
+  options_t& options = elliptic->options;
+  elliptic->splitOverlap = false;
+  if (!elliptic->overlap) return NRSB_OK;
+  if (options.compareArgs("ENABLE GS COMM OVERLAP", "UNSPLIT")) return NRSB_OK;
+  if (options.compareArgs("ENABLE GS COMM OVERLAP", "SPLIT")) {
+    elliptic->splitOverlap = true;
+    return NRSB_OK;
+  }
+  if (!options.compareArgs("ENABLE GS COMM OVERLAP", "TIMED")) return NRSB_OK;
+  if (elliptic->lambdaField && !elliptic->o_lambda0Field) return NRSB_OK;  // coefficient fields arrive after setup
+  const size_t n = (size_t)elliptic->fieldOffset * elliptic->Nfields;
+  int rc;
+  for (int split = 0; split < 2; ++split) {
+    elliptic->splitOverlap = split != 0;
+    if (precision == 8) {
+      dbuf<double> q, Aq;
+      if ((rc = q.alloc(n)) || (rc = Aq.alloc(n))) return rc;
+      if ((rc = time_operator<double>(elliptic, q.p, Aq.p, &elliptic->overlapTimes[split]))) return rc;
+    } else {
+      dbuf<float> q, Aq;
+      if ((rc = q.alloc(n)) || (rc = Aq.alloc(n))) return rc;
+      if ((rc = time_operator<float>(elliptic, q.p, Aq.p, &elliptic->overlapTimes[split]))) return rc;
+    }
+  }
+  elliptic->splitOverlap = elliptic->overlapTimes[1] < elliptic->overlapTimes[0];
+  if ((!elliptic->mesh->comm || elliptic->mesh->comm->rank == 0) && getenv("NRSB_VERBOSE"))
+    fprintf(stderr, "testing Ax overlap (N=%d, %s): unsplit %.2es split %.2es (%s)\n", elliptic->mesh->N,
+            precision == 8 ? "fp64" : "fp32", elliptic->overlapTimes[0], elliptic->overlapTimes[1],
+            elliptic->splitOverlap ? "split" : "unsplit");
+  return NRSB_OK;
+}
 
 int ellipticZeroMean(elliptic_t* elliptic, double* o_q)
 {
@@ -563,6 +633,7 @@ int ellipticSolveSetup(elliptic_t* elliptic)
                       mesh->NlocalGatherElements > 0;
 
   if ((rc = ellipticKrylovWorkspace(elliptic))) return rc;
+  if ((rc = ellipticChooseOverlap(elliptic, 8))) return rc;
 
   if ((rc = ellipticPreconditionerSetup(elliptic))) return rc;
 

@@ -348,6 +348,11 @@ class elliptic_t {
   std::unique_ptr<ogs_t> ogs;
   std::unique_ptr<oogs_t> oogs;
   bool overlap = false;  // oogsAx != oogs in the reference: split Ax into halo / interior elements
+  // which form ellipticOperator takes on several ranks: the reference's split (Ax halo, oogs::start, Ax interior,
+  // oogs::finish) or Ax on all elements + the one-launch exchange.  ENABLE GS COMM OVERLAP = SPLIT / UNSPLIT fix it,
+  // TIMED measures both at setup and keeps the faster (ellipticSetup.cpp:255-302, ellipticMultiGridSetup.cpp:123)
+  bool splitOverlap = false;
+  double overlapTimes[2] = {0.0, 0.0};  // TIMED: seconds per operator {unsplit, split}, max over ranks
   dbuf<double> o_resHist;  // device-side residual history of the current PCG solve
   bool fusedHaloAx = true;  // overlap through ONE launch (axhelm + in-kernel halo push) when Nq == 8
   // mask + on-rank gather-scatter as phase 2 of the axhelm launch when Nq == 8 (struct FusedRows, gs.hpp)
@@ -406,6 +411,7 @@ class elliptic_t {
 
 // elliptic.cpp
 int ellipticSolveSetup(elliptic_t* elliptic);
+int ellipticChooseOverlap(elliptic_t* elliptic, int precision);
 int ellipticKrylovWorkspace(elliptic_t* elliptic);  // (re)sizes the PGMRES buffers for the current SOLVER options
 int ellipticSolve(elliptic_t* elliptic, double* o_r, double* o_x);
 template <typename T>

@@ -991,7 +991,7 @@ static int build_level_elliptic(elliptic_t* base, mesh_t* baseMesh, int Nc, std:
   if ((rc = ellipticOgs(mesh, e->EToB, e))) return rc;
   e->overlap = e->ogs->NhaloGather > 0 && !e->options.compareArgs("ENABLE GS COMM OVERLAP", "FALSE") &&
                mesh->NlocalGatherElements > 0;
-  return NRSB_OK;
+  return ellipticChooseOverlap(e, 4);
 }
 
 int ellipticMultiGridSetup(elliptic_t* elliptic_, precon_t* precon)

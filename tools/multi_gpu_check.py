@@ -127,6 +127,19 @@ def main():
     errf = np.max(np.abs(d_Aqf.download(np.float32)[:nloc] - out_ref_f[gnode])) / np.max(np.abs(out_ref_f))
     report("fp32 operator (one-launch exchange) vs oracle", errf < 1e-5, "relerr %.2e" % errf)
     ell_ll.destroy()
+    # ENABLE GS COMM OVERLAP = TIMED: both forms are measured at setup (10 applications each, max over ranks) and every
+    # rank keeps the same one (ellipticSetup.cpp:255-302); whichever it is, the result has the same bits
+    opts_t = dict(opts_ll)
+    opts_t["ENABLE GS COMM OVERLAP"] = "TIMED"
+    ell_t = Elliptic(part, opts_t, comm=comm, topo_of=topo_of)
+    tu, ts, pick = ell_t.get_real("overlapTimeUnsplit"), ell_t.get_real("overlapTimeSplit"), ell_t.get_int("splitOverlap")
+    picks = comm.allreduce_sum(np.array([float(pick)]))[0]
+    report("timed overlap choice", tu > 0 and ts > 0 and pick == (1 if ts < tu else 0) and picks in (0.0, float(world)),
+           "unsplit %.1f us split %.1f us -> %s" % (tu * 1e6, ts * 1e6, "split" if pick else "unsplit"))
+    d_Aq4 = DB.zeros(ell.fieldOffset, np.float64)
+    ell_t.operator(d_q, d_Aq4)
+    report("timed choice == split path", np.array_equal(d_Aq4.download()[:nloc], d_Aq2.download()[:nloc]))
+    ell_t.destroy()
     rhs_glob = meshgen.kershaw_rhs(whole)
     ref.solve(rhs_glob, np.zeros_like(rhs_glob))
     x = np.zeros(nloc)
