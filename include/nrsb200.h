@@ -119,6 +119,15 @@ int nrsb_ellipticBlockPartialAxCoeffHex3D(int Nq, int precision, nrsb_dlong Nele
                                           nrsb_dlong loffset, const nrsb_dlong* d_elementList, const void* d_ggeo,
                                           const void* D_host, const void* d_lambda0, const void* d_lambda1,
                                           int lambdaField, const void* d_q, void* d_Aq, void* stream);
+/* ellipticStressPartialAxCoeffHex3D (kernels/elliptic/ellipticStressPartialAxCoeffHex3D.okl, serial twin .c:1-169;
+ * the AxKernel of a block solver with stressForm, ellipticSetup.cpp:240-249): the coupled viscous-stress operator
+ * A (u,v,w) = -div(lambda0 (grad q + grad q^T)) + lambda1 q in weak form.  d_vgeo: 12 planes per element in the
+ * reference's order (rx,ry,rz,sx,sy,sz,tx,ty,tz,J,JW,1/JW: mesh3D.h:82-93); fields `offset` apart, coefficients at
+ * lambda[p_lambda*id + f*loffset]. */
+int nrsb_ellipticStressPartialAxCoeffHex3D(int Nq, int precision, nrsb_dlong Nelements, nrsb_dlong offset,
+                                           nrsb_dlong loffset, const nrsb_dlong* d_elementList, const void* d_vgeo,
+                                           const void* D_host, const void* d_lambda0, const void* d_lambda1,
+                                           int lambdaField, const void* d_q, void* d_Aq, void* stream);
 /* ellipticBlockBuildDiagonalHex3D (kernels/elliptic/ellipticBlockBuildDiagonalHex3D.okl; ellipticUpdateJacobi.cpp:
  * 38-47,66-75): Aq[id + l*offset] = diag(D^T lambda0 G D)[id] (+ lambda1 GwJ), l < Nfields.  lambdaField = 1:
  * lambda0/lambda1 are per-node fields read at id + l*loffset (the reference's layout), 0: one value each.

@@ -396,6 +396,22 @@ int nrsb_ellipticBlockPartialAxCoeffHex3D(int Nq, int precision, nrsb_dlong Nele
                                       (const float*)D_host, (const float*)d_lambda0, (const float*)d_lambda1,
                                       lambdaField, (const float*)d_q, (float*)d_Aq, ST(stream));
 }
+int nrsb_ellipticStressPartialAxCoeffHex3D(int Nq, int precision, nrsb_dlong Nelements, nrsb_dlong offset,
+                                           nrsb_dlong loffset, const nrsb_dlong* d_elementList, const void* d_vgeo,
+                                           const void* D_host, const void* d_lambda0, const void* d_lambda1,
+                                           int lambdaField, const void* d_q, void* d_Aq, void* stream)
+{
+  PREC_OK(precision);
+  NRSB_REQUIRE(D_host && (Nelements == 0 || (d_elementList && d_vgeo && d_lambda0 && d_lambda1 && d_q && d_Aq)),
+               "NULL argument");
+  return precision == 8
+             ? ax_stress_launch<double>(Nq, Nelements, offset, loffset, d_elementList, (const double*)d_vgeo,
+                                        (const double*)D_host, (const double*)d_lambda0, (const double*)d_lambda1,
+                                        lambdaField, (const double*)d_q, (double*)d_Aq, ST(stream))
+             : ax_stress_launch<float>(Nq, Nelements, offset, loffset, d_elementList, (const float*)d_vgeo,
+                                       (const float*)D_host, (const float*)d_lambda0, (const float*)d_lambda1,
+                                       lambdaField, (const float*)d_q, (float*)d_Aq, ST(stream));
+}
 int nrsb_ellipticBlockBuildDiagonalHex3D(int Nq, int precision, nrsb_dlong Nelements, int Nfields, nrsb_dlong offset,
                                          nrsb_dlong loffset, const void* d_ggeo, const void* D_host,
                                          const void* d_lambda0, const void* d_lambda1, int poisson, int lambdaField,

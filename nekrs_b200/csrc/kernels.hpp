@@ -19,6 +19,11 @@ template <typename T>
 int ax_block_launch(int Nq, int variant, dlong Nelements, int Nfields, dlong offset, dlong loffset,
                     const dlong* elementList, const T* ggeo, const T* D_host, const T* lambda0, const T* lambda1,
                     int lambdaField, const T* q, T* Aq, cudaStream_t stream);
+// ellipticStressPartialAxCoeffHex3D (stress.cu): three coupled fields, vgeo = 12 planes per element
+template <typename T>
+int ax_stress_launch(int Nq, dlong Nelements, dlong offset, dlong loffset, const dlong* elementList, const T* vgeo,
+                     const T* D_host, const T* lambda0, const T* lambda1, int lambdaField, const T* q, T* Aq,
+                     cudaStream_t stream);
 int ax_default_variant(int Nq, int precision);
 struct FusedHalo;
 template <typename T>

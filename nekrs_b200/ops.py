@@ -224,6 +224,16 @@ def linalg_many(name, prec, *args, stream=None):
     call("nrsb_" + name, *conv)
 
 
+def ellipticStressPartialAxCoeffHex3D(N, Nelements, offset, loffset, element_list, vgeo, D_host, lambda0, lambda1, q, Aq,
+                                      *, lambda_field=False, dtype=np.float64, stream=None):
+    """AxKernel of a stress-form block solver (ellipticStressPartialAxCoeffHex3D.okl); vgeo = 12 planes per element."""
+    prec = 8 if np.dtype(dtype) == np.float64 else 4
+    D_host = np.ascontiguousarray(D_host, dtype=dtype)
+    call("nrsb_ellipticStressPartialAxCoeffHex3D", C.c_int(N + 1), C.c_int(prec), i32(Nelements), i32(offset),
+         i32(loffset), vp(element_list), vp(vgeo), vp(D_host), vp(lambda0), vp(lambda1),
+         C.c_int(1 if lambda_field else 0), vp(q), vp(Aq), vp(stream))
+
+
 def ellipticBlockPartialAxCoeffHex3D(N, Nelements, offset, loffset, element_list, ggeo, D_host, lambda0, lambda1, q, Aq,
                                      *, lambda_field=False, dtype=np.float64, stream=None):
     prec = 8 if np.dtype(dtype) == np.float64 else 4

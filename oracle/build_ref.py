@@ -98,6 +98,16 @@ def ref_ax_block(N: int, lambda_field: int) -> str:
     return _compile("axblock_d_N%d_lambda%d" % (N, lambda_field), ["elliptic/ellipticBlockPartialAxCoeffHex3D.c"], d)
 
 
+def ref_ax_stress(N: int, lambda_field: int) -> str:
+    """ellipticStressPartialAxCoeffHex3D_v0 (three coupled fields, vgeo ids of src/mesh/mesh3D.h:82-93)."""
+    Nq = N + 1
+    d = _common_defs(Nq)
+    d.update({"dfloat": "double", "pfloat": "float", "p_knl": 0, "p_lambda": lambda_field, "p_Nfields": 3,
+              "p_Nvgeo": 12, "p_RXID": 0, "p_RYID": 1, "p_RZID": 2, "p_SXID": 3, "p_SYID": 4, "p_SZID": 5,
+              "p_TXID": 6, "p_TYID": 7, "p_TZID": 8, "p_JID": 9, "p_JWID": 10, "p_IJWID": 11})
+    return _compile("axstress_d_N%d_lambda%d" % (N, lambda_field), ["elliptic/ellipticStressPartialAxCoeffHex3D.c"], d)
+
+
 def ref_fdm(N: int, restrict: int, fast: bool = False) -> str:
     Nq = N + 1
     d = _common_defs(Nq)
@@ -142,6 +152,8 @@ def build_ref(fast: bool = True) -> bool:
     for N in (3, 7):
         ref_ax_block(N, 0)
         ref_ax_block(N, 1)
+        ref_ax_stress(N, 0)
+        ref_ax_stress(N, 1)
     for N in FDM_ORDERS:
         ref_fdm(N, 1)
         ref_fdm(N, 0)

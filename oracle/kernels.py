@@ -81,6 +81,16 @@ class Orc:
                _p(q[f * offset:]), _p(Aq[f * offset:]), c_int(Nq), c_int(0), c_int(1 if lambda_field else 0))
         return Aq
 
+    def ax_stress(self, N, element_list, vgeo, D, q, Aq, lambda0, lambda1, offset, loffset, lambda_field=False):
+        """ellipticStressPartialAxCoeffHex3D.c:1-169: three coupled fields, stress form; vgeo = 12 planes per
+        element (rx..tz, J, JW, 1/JW)."""
+        dt = q.dtype
+        fn = getattr(self.lib, "orc_ax_stress_" + self._suf(q))
+        fn(c_int(len(element_list)), c_int(offset), c_int(loffset), _p(_chk(element_list, np.int32)),
+           _p(_chk(vgeo, dt)), _p(_chk(D, dt)), _p(_chk(lambda0, dt)), _p(_chk(lambda1, dt)), _p(_chk(q, dt)),
+           _p(_chk(Aq, dt)), c_int(N + 1), c_int(1 if lambda_field else 0))
+        return Aq
+
     def mask(self, mask_ids, q):
         getattr(self.lib, "orc_mask_" + self._suf(q))(c_int(len(mask_ids)), _p(_chk(mask_ids, np.int32)), _p(q))
 
@@ -213,6 +223,19 @@ class RefAxBlock:
         S = np.ascontiguousarray(D.T)
         self.lib.ellipticBlockPartialAxCoeffHex3D_v0(_r(len(element_list)), _r(offset), _r(loffset), _p(element_list),
                                                      _p(ggeo), _p(D), _p(S), _p(lambda0), _p(lambda1), _p(q), _p(Aq))
+        return Aq
+
+
+class RefAxStress:
+    """ellipticStressPartialAxCoeffHex3D_v0 compiled from the reference (three coupled fields)."""
+
+    def __init__(self, N, lambda_field):
+        self.lib = _ref("axstress_d_N%d_lambda%d" % (N, 1 if lambda_field else 0))
+
+    def __call__(self, element_list, vgeo, D, q, Aq, lambda0, lambda1, offset, loffset):
+        S = np.ascontiguousarray(D.T)
+        self.lib.ellipticStressPartialAxCoeffHex3D_v0(_r(len(element_list)), _r(offset), _r(loffset), _p(element_list),
+                                                      _p(vgeo), _p(D), _p(S), _p(lambda0), _p(lambda1), _p(q), _p(Aq))
         return Aq
 
 

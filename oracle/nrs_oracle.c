@@ -99,6 +99,92 @@ DEF_AX(double, d)
 DEF_AX(float, f)
 
 /* ------------------------------------------------------------------------- */
+/* ellipticStressPartialAxCoeffHex3D_v0   kernels/elliptic/ellipticStressPartialAxCoeffHex3D.c:1-169
+ * three coupled fields (u, v, w `offset` apart), viscous stress form
+ *     A q = -div( lambda0 (grad q + grad q^T) ) + lambda1 q       (weak form, collocated JW)
+ * vgeo planes: rx,ry,rz,sx,sy,sz,tx,ty,tz = 0..8, J = 9, JW = 10, 1/JW = 11 (src/mesh/mesh3D.h:82-93),
+ * coefficients per field `loffset` apart, per node when p_lambda = 1.
+ * Restated as three passes over the element (reference derivatives -> stress fluxes -> weak divergence); every
+ * scalar is accumulated in the reference's order (m ascending; the three directions of the divergence interleaved
+ * in ONE accumulator, :139-151), so the result has the reference's bits at -O2.                                 */
+#define DEF_AX_STRESS(T, SUF)                                                                        \
+  void orc_ax_stress_##SUF(dlong Nelements, dlong offset, dlong loffset, const dlong *elementList,   \
+                           const T *vgeo, const T *D, const T *lambda0, const T *lambda1, const T *q, \
+                           T *Aq, int Nq, int p_lambda)                                              \
+  {                                                                                                  \
+    const int Np = Nq * Nq * Nq, Nq2 = Nq * Nq;                                                      \
+    T *fld = (T *)malloc(12 * (size_t)Np * sizeof(T)); /* 3 fields + 9 fluxes */                     \
+    T *flux = fld + 3 * Np;                            /* [field][direction r,s,t][Np] */            \
+    for (dlong el = 0; el < Nelements; ++el) {                                                       \
+      const dlong e = elementList[el];                                                               \
+      const T *g = vgeo + (size_t)e * Np * 12;                                                       \
+      for (int f = 0; f < 3; ++f)                                                                    \
+        for (int n = 0; n < Np; ++n)                                                                 \
+          fld[f * Np + n] = q[(size_t)e * Np + n + (size_t)f * offset];                              \
+      for (int k = 0; k < Nq; ++k)                                                                   \
+        for (int j = 0; j < Nq; ++j)                                                                 \
+          for (int i = 0; i < Nq; ++i) {                                                             \
+            const int n = k * Nq2 + j * Nq + i;                                                      \
+            T dr[3], ds[3], dt[3]; /* reference derivatives of the three fields */                   \
+            for (int f = 0; f < 3; ++f) {                                                            \
+              const T *s = fld + f * Np;                                                             \
+              T a = 0, b = 0, c = 0;                                                                 \
+              for (int m = 0; m < Nq; ++m) {                                                         \
+                a += D[i * Nq + m] * s[k * Nq2 + j * Nq + m];                                        \
+                b += D[j * Nq + m] * s[k * Nq2 + m * Nq + i];                                        \
+                c += D[k * Nq + m] * s[m * Nq2 + j * Nq + i];                                        \
+              }                                                                                      \
+              dr[f] = a;                                                                             \
+              ds[f] = b;                                                                             \
+              dt[f] = c;                                                                             \
+            }                                                                                        \
+            const T rx = g[0 * Np + n], ry = g[1 * Np + n], rz = g[2 * Np + n];                      \
+            const T sx = g[3 * Np + n], sy = g[4 * Np + n], sz = g[5 * Np + n];                      \
+            const T tx = g[6 * Np + n], ty = g[7 * Np + n], tz = g[8 * Np + n];                      \
+            const T JW = g[10 * Np + n];                                                             \
+            T grad[3][3]; /* grad[f][x,y,z] */                                                       \
+            for (int f = 0; f < 3; ++f) {                                                            \
+              grad[f][0] = rx * dr[f] + sx * ds[f] + tx * dt[f];                                     \
+              grad[f][1] = ry * dr[f] + sy * ds[f] + ty * dt[f];                                     \
+              grad[f][2] = rz * dr[f] + sz * ds[f] + tz * dt[f];                                     \
+            }                                                                                        \
+            const dlong id = e * Np + n;                                                             \
+            for (int f = 0; f < 3; ++f) {                                                            \
+              const T lam0 = lambda0[p_lambda * id + f * loffset];                                   \
+              const T s1 = lam0 * JW * (grad[f][0] + grad[0][f]);                                    \
+              const T s2 = lam0 * JW * (grad[f][1] + grad[1][f]);                                    \
+              const T s3 = lam0 * JW * (grad[f][2] + grad[2][f]);                                    \
+              flux[(3 * f + 0) * Np + n] = rx * s1 + ry * s2 + rz * s3;                              \
+              flux[(3 * f + 1) * Np + n] = sx * s1 + sy * s2 + sz * s3;                              \
+              flux[(3 * f + 2) * Np + n] = tx * s1 + ty * s2 + tz * s3;                              \
+            }                                                                                        \
+          }                                                                                          \
+      for (int k = 0; k < Nq; ++k)                                                                   \
+        for (int j = 0; j < Nq; ++j)                                                                 \
+          for (int i = 0; i < Nq; ++i) {                                                             \
+            const int n = k * Nq2 + j * Nq + i;                                                      \
+            const dlong id = e * Np + n;                                                             \
+            const T JW = g[10 * Np + n];                                                             \
+            for (int f = 0; f < 3; ++f) {                                                            \
+              const T *Fr = flux + (3 * f + 0) * Np, *Fs = flux + (3 * f + 1) * Np,                  \
+                      *Ft = flux + (3 * f + 2) * Np;                                                 \
+              T acc = 0;                                                                             \
+              for (int m = 0; m < Nq; ++m) {                                                         \
+                acc += D[m * Nq + i] * Fr[k * Nq2 + j * Nq + m];                                     \
+                acc += D[m * Nq + j] * Fs[k * Nq2 + m * Nq + i];                                     \
+                acc += D[m * Nq + k] * Ft[m * Nq2 + j * Nq + i];                                     \
+              }                                                                                      \
+              const T lam1 = lambda1[p_lambda * id + f * loffset];                                   \
+              Aq[id + (size_t)f * offset] = acc + lam1 * JW * fld[f * Np + n];                       \
+            }                                                                                        \
+          }                                                                                          \
+    }                                                                                                \
+    free(fld);                                                                                       \
+  }
+DEF_AX_STRESS(double, d)
+DEF_AX_STRESS(float, f)
+
+/* ------------------------------------------------------------------------- */
 /* mask   kernels/core/mask.okl : q[maskIds[n]] = 0                          */
 #define DEF_MASK(T, SUF)                                            \
   void orc_mask_##SUF(dlong Nmasked, const dlong *maskIds, T *q)    \

@@ -485,3 +485,39 @@ def test_block_axhelm(orc, N, dt, lambda_field):
     untouched = np.setdiff1d(np.arange(E), el)
     for f in range(3):
         assert np.all(out[f * offset:f * offset + E * Np].reshape(E, Np)[untouched] == -3.0)
+
+
+@pytest.mark.parametrize("N", [1, 3, 4, 7, 9, 11])
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("lambda_field", [False, True])
+def test_stress_axhelm(orc, N, dt, lambda_field):
+    """ellipticStressPartialAxCoeffHex3D: the coupled viscous-stress operator on three fields (the oracle is pinned
+    bit-exact to the reference's kernel in tests/test_oracle_vs_ref.py)."""
+    if N == 11 and dt == np.float64:
+        E = 5
+    else:
+        E = 19
+    Np = (N + 1) ** 3
+    r = rng(80 + N)
+    g, _ = sem.jacobi_gll(N)
+    D = sem.dmatrix_1d(g).astype(dt)
+    vgeo = (r.random((E, 12, Np)) - 0.3).astype(dt)
+    offset, loffset = E * Np + 24, E * Np + 8
+    q = r.random(3 * offset).astype(dt)
+    if lambda_field:
+        lam0, lam1 = (r.random(3 * loffset) + 0.5).astype(dt), r.random(3 * loffset).astype(dt)
+    else:
+        lam0, lam1 = np.zeros(3 * loffset, dt), np.zeros(3 * loffset, dt)
+        lam0[[0, loffset, 2 * loffset]] = [1.1, 1.2, 1.3]
+        lam1[[0, loffset, 2 * loffset]] = [0.5, 0.6, 0.7]
+    el = r.permutation(E)[: E - 2].astype(np.int32)
+    ref = np.full(3 * offset, -3.0, dtype=dt)
+    orc.ax_stress(N, el, vgeo, D, q, ref, lam0, lam1, offset, loffset, lambda_field=lambda_field)
+    d_Aq = DB(like=np.full(3 * offset, -3.0, dtype=dt))
+    ops.ellipticStressPartialAxCoeffHex3D(N, el.size, offset, loffset, DB(like=el), DB(like=vgeo), D, DB(like=lam0),
+                                          DB(like=lam1), DB(like=q), d_Aq, lambda_field=lambda_field, dtype=dt)
+    out = d_Aq.download(dt)
+    assert relerr(out, ref) < TOL[dt] * (10 if dt == np.float32 else 1)
+    untouched = np.setdiff1d(np.arange(E), el)
+    for f in range(3):
+        assert np.all(out[f * offset:f * offset + E * Np].reshape(E, Np)[untouched] == -3.0)

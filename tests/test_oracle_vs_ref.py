@@ -201,3 +201,84 @@ def test_block_ax_oracle_equals_reference_bit_exact(orc, N, lambda_field):
     orc.ax_block(N, el, ggeo, D, q, a, lam0, lam1, offset, loffset, lambda_field=lambda_field)
     K.RefAxBlock(N, lambda_field)(el, ggeo, D, q, b, lam0, lam1, offset, loffset)
     assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("N", [3, 7])
+@pytest.mark.parametrize("lambda_field", [False, True])
+def test_stress_ax_oracle_equals_reference_bit_exact(orc, N, lambda_field):
+    """The coupled three-field stress operator (ellipticStressPartialAxCoeffHex3D.c): the oracle's three-pass
+    restatement keeps every accumulation in the reference's order; bit-identical to the reference kernel compiled in
+    place."""
+    from oracle import kernels as K
+    name = "axstress_d_N%d_lambda%d" % (N, 1 if lambda_field else 0)
+    if not K.ref_available(name):
+        pytest.skip("reference kernels not built here")
+    E, Np = 7, (N + 1) ** 3
+    r = np.random.Generator(np.random.PCG64(60 + N))
+    g, _ = sem.jacobi_gll(N)
+    D = sem.dmatrix_1d(g)
+    vgeo = r.random((E, 12, Np)) - 0.3
+    offset, loffset = E * Np + 16, E * Np + 8
+    q = r.random(3 * offset)
+    if lambda_field:
+        lam0, lam1 = r.random(3 * loffset) + 0.5, r.random(3 * loffset)
+    else:
+        lam0, lam1 = np.zeros(3 * loffset), np.zeros(3 * loffset)
+        lam0[[0, loffset, 2 * loffset]] = [1.1, 1.2, 1.3]
+        lam1[[0, loffset, 2 * loffset]] = [0.5, 0.6, 0.7]
+    el = r.permutation(E).astype(np.int32)[:5]
+    a = np.full(3 * offset, -2.0)
+    b = a.copy()
+    orc.ax_stress(N, el, vgeo, D, q, a, lam0, lam1, offset, loffset, lambda_field=lambda_field)
+    K.RefAxStress(N, lambda_field)(el, vgeo, D, q, b, lam0, lam1, offset, loffset)
+    assert np.array_equal(a, b)
+    untouched = np.setdiff1d(np.arange(E), el)
+    assert np.all(a[:E * Np].reshape(E, Np)[untouched] == -2.0)
+
+
+def test_stress_ax_symmetric_and_rigid_motions(orc):
+    """Properties of the stress form on a real mesh (vgeo from the trilinear map of a kershaw box, computed here):
+    the element operator is symmetric, and rigid translations have zero stress (lambda1 = 0)."""
+    from nekrs_b200 import meshgen
+    N = 3
+    m = meshgen.box_mesh(N, (2, 2, 1), kershaw_eps=0.5)
+    E, Np, Nq = m.Nelements, m.Np, N + 1
+    g, w = sem.jacobi_gll(N)
+    D = sem.dmatrix_1d(g)
+    vgeo = np.zeros((E, 12, Np))
+    X = [np.asarray(c).reshape(E, Nq, Nq, Nq) for c in (m.x, m.y, m.z)]
+    dr = lambda f: np.einsum("im,ekjm->ekji", D, f)
+    ds = lambda f: np.einsum("jm,ekmi->ekji", D, f)
+    dtt = lambda f: np.einsum("km,emji->ekji", D, f)
+    J = np.empty((E, Nq, Nq, Nq, 3, 3))
+    for a, f in enumerate(X):
+        J[..., a, 0], J[..., a, 1], J[..., a, 2] = dr(f), ds(f), dtt(f)
+    Ji = np.linalg.inv(J)            # rows r,s,t ; columns x,y,z
+    det = np.linalg.det(J)
+    for a in range(3):
+        for b in range(3):
+            vgeo[:, 3 * a + b] = Ji[..., a, b].reshape(E, Np)
+    W = (w[:, None, None] * w[None, :, None] * w[None, None, :]).reshape(1, Np)
+    vgeo[:, 9] = det.reshape(E, Np)
+    vgeo[:, 10] = det.reshape(E, Np) * W
+    vgeo[:, 11] = 1.0 / vgeo[:, 10]
+    offset = loffset = E * Np
+    el = np.arange(E, dtype=np.int32)
+    lam0 = np.zeros(3 * loffset)
+    lam1 = np.zeros(3 * loffset)
+    lam0[[0, loffset, 2 * loffset]] = 1.0
+    r = np.random.Generator(np.random.PCG64(5))
+    x1, x2 = r.random(3 * offset), r.random(3 * offset)
+    A1, A2 = np.zeros(3 * offset), np.zeros(3 * offset)
+    orc.ax_stress(N, el, vgeo, D, x1, A1, lam0, lam1, offset, loffset)
+    orc.ax_stress(N, el, vgeo, D, x2, A2, lam0, lam1, offset, loffset)
+    assert abs(np.dot(x2, A1) - np.dot(x1, A2)) < 1e-11 * abs(np.dot(x2, A1))
+    t = np.concatenate([np.full(offset, 0.3), np.full(offset, -1.2), np.full(offset, 2.0)])
+    At = np.zeros(3 * offset)
+    orc.ax_stress(N, el, vgeo, D, t, At, lam0, lam1, offset, loffset)
+    assert np.max(np.abs(At)) < 1e-11 * np.max(np.abs(A1))
+    # rigid rotation about z: u = -y, v = x, w = 0  ->  symmetric gradient vanishes
+    rot = np.concatenate([-np.asarray(m.y).ravel(), np.asarray(m.x).ravel(), np.zeros(offset)])
+    Ar = np.zeros(3 * offset)
+    orc.ax_stress(N, el, vgeo, D, rot, Ar, lam0, lam1, offset, loffset)
+    assert np.max(np.abs(Ar)) < 1e-10 * np.max(np.abs(A1))
