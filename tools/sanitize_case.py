@@ -36,6 +36,38 @@ def main():
     x2 = np.zeros(small.Nelements * small.Np)
     e2.solve_host(meshgen.kershaw_rhs(small), x2)
     print("BPS5 iterations", e2.Niter)
+    # the coarse solve on all SMs (grid barrier) instead of the cluster kernel
+    import ctypes
+    from nekrs_b200 import lib, ops
+    lib.call("nrsb_set_coarse_variant", ctypes.c_int(3))
+    x2[:] = 0
+    e2.solve_host(meshgen.kershaw_rhs(small), x2)
+    lib.call("nrsb_set_coarse_variant", ctypes.c_int(1))
+    print("BPS5 iterations (grid coarse kernel)", e2.Niter, "grid", e2.get_int("coarseGridSize"))
+    # TMA ring with padded consumer groups (Nq = 6 fp64, Nq = 10 fp32) and the stress operator
+    from oracle import sem
+    r = np.random.Generator(np.random.PCG64(2))
+    for N, dt, E in ((5, np.float64, 1900), (9, np.float32, 700)):
+        Np = (N + 1) ** 3
+        g, _ = sem.jacobi_gll(N)
+        D = sem.dmatrix_1d(g).astype(dt)
+        d_Aq = DB.zeros(E * Np, dt)
+        ops.ellipticPartialAxCoeffHex3D(N, DB(like=np.arange(E, dtype=np.int32)), DB(like=r.random(E * 7 * Np).astype(dt)),
+                                        D, DB(like=r.random(E * Np).astype(dt)), d_Aq, Nelements=E,
+                                        lambda0=DB(like=np.ones(1, dt)), variant=4, dtype=dt)
+        print("TMA ring N=%d %s" % (N, np.dtype(dt).name), float(np.abs(d_Aq.download(dt)).max()) > 0)
+    N, E = 7, 40
+    Np = 512
+    g, _ = sem.jacobi_gll(N)
+    D = sem.dmatrix_1d(g)
+    off = E * Np
+    lam = np.zeros(3 * off)
+    lam[[0, off, 2 * off]] = 1.0
+    d_Aq = DB.zeros(3 * off, np.float64)
+    ops.ellipticStressPartialAxCoeffHex3D(N, E, off, off, DB(like=np.arange(E, dtype=np.int32)),
+                                          DB(like=r.random(E * 12 * Np)), D, DB(like=lam), DB(like=lam),
+                                          DB(like=r.random(3 * off)), d_Aq)
+    print("stress operator", float(np.abs(d_Aq.download()).max()) > 0)
 
 
 if __name__ == "__main__":
