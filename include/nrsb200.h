@@ -265,6 +265,16 @@ typedef struct {
   double lambda0, lambda1;      /* constant coefficients (o_lambda0/o_lambda1) */
   nrsb_comm_t comm;             /* NULL on one rank */
   const char* name;             /* "pressure" */
+  /* block solver (elliptic->Nfields, elliptic->stressForm; ellipticSetup.cpp:81-131,209-249).  Nfields = 0 or 1: scalar
+   * solve.  Nfields = 3: three fields `fieldOffset` apart in every vector, EToB then holds Nfields*Nelements*6 flags
+   * (field-major, as elliptic->EToB), PRECONDITIONER = JACOBI or NONE, SOLVER = PCG; stressForm selects
+   * ellipticStressPartialAxCoeffHex3D instead of ellipticBlockPartialAxCoeffHex3D.  blockLambda0/1: HOST, one constant
+   * per field (NULL: lambda0/lambda1 for every field); per-node fields go through nrsb_elliptic_set_coeff_field with
+   * loffset = fieldOffset. */
+  int Nfields;
+  int stressForm;
+  const double* blockLambda0;
+  const double* blockLambda1;
 } nrsb_elliptic_config;
 
 /* ellipticSolveSetup (ellipticSetup.cpp:116-327) */

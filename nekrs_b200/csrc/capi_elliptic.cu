@@ -200,7 +200,11 @@ int nrsb_elliptic_setup(const nrsb_elliptic_config* cfg, nrsb_elliptic_t* out)
   e.poisson = cfg->poisson != 0;
   e.lambda0Value = cfg->lambda0;
   e.lambda1Value = cfg->lambda1;
-  e.EToB.assign(cfg->EToB, cfg->EToB + (size_t)cfg->Nelements * 6);
+  e.Nfields = cfg->Nfields > 1 ? cfg->Nfields : 1;
+  e.stressForm = cfg->stressForm != 0;
+  e.EToB.assign(cfg->EToB, cfg->EToB + (size_t)cfg->Nelements * 6 * e.Nfields);
+  if (e.Nfields > 1 && cfg->blockLambda0) e.blockLambda0.assign(cfg->blockLambda0, cfg->blockLambda0 + e.Nfields);
+  if (e.Nfields > 1 && cfg->blockLambda1) e.blockLambda1.assign(cfg->blockLambda1, cfg->blockLambda1 + e.Nfields);
   parse_options(cfg->options, e.options);
   for (int l = 0; l < cfg->nLevels; ++l) {
     const int Nc = cfg->levelOrders[l];
@@ -248,6 +252,7 @@ int nrsb_elliptic_solve_host(nrsb_elliptic_t h, const double* rhs_host, double* 
                              double* res0Norm, double* resNorm)
 {
   NRSB_REQUIRE(h && rhs_host && x_host, "NULL argument");
+  NRSB_REQUIRE(h->impl.Nfields == 1, "block solves take device vectors (nrsb_elliptic_solve)");
   int rc = ensure_staging(h);
   if (rc) return rc;
   cudaStream_t st = h->impl.stream;
@@ -570,7 +575,8 @@ int nrsb_elliptic_get_array(nrsb_elliptic_t h, const char* key, void* out_host, 
     return NRSB_ERR_INVALID;
   }
   if (k == "invDiagA" && e.precon && e.precon->o_invDiagA.p)
-    return out_dev(e.precon->o_invDiagA.p, (size_t)e.mesh->Nlocal, out_host, capacity, count);
+    return out_dev(e.precon->o_invDiagA.p, e.Nfields == 1 ? (size_t)e.mesh->Nlocal : (size_t)e.Nvec(), out_host,
+                   capacity, count);
   if (k == "maskIds") return out_vec(e.maskIds, out_host, capacity, count);
   if (k == "invDegree") return out_vec(e.ogs->invDegree, out_host, capacity, count);
   if (k == "meshInvDegree") return out_vec(e.mesh->ogs->invDegree, out_host, capacity, count);

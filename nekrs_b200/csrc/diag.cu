@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(Nq* Nq)
     for (int m = 0; m < Nq; ++m) {
       const int n = m * Nq * Nq + j * Nq + i;
       r_Gtt[m] = g[5 * Np + n];
-      r_lambdat[m] = kLambdaField ? lambda0[(size_t)e * Np + n + (size_t)l * loffset] : lambda0[0];
+      r_lambdat[m] = lambda0[(kLambdaField ? (size_t)e * Np + n : 0) + (size_t)l * loffset];
     }
 #pragma unroll
     for (int k = 0; k < Nq; ++k) {
@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(Nq* Nq)
         r_q += r_Gtt[m] * r_lambdat[m] * Dm.v[m * Nq + k] * Dm.v[m * Nq + k];
       }
       if constexpr (!kPoisson) {
-        const T lbda_1 = kLambdaField ? lambda1[(size_t)e * Np + n + (size_t)l * loffset] : lambda1[0];
+        const T lbda_1 = lambda1[(kLambdaField ? (size_t)e * Np + n : 0) + (size_t)l * loffset];
         r_q += g[6 * Np + n] * lbda_1;
       }
       Aq[(size_t)e * Np + n + (size_t)l * offset] = r_q;

@@ -72,8 +72,72 @@ static void face_nodes(int N, std::vector<std::vector<int>>& fn)
   }
 }
 
+// ellipticOgs for a block solver (ellipticOgs.cpp:17-131 with nFields > 1; ellipticSetup.cpp:192-226): boundary flags
+// per field (EToB[f + 6 e + fld * 6 E]), mask ids n + fld * fieldOffset, and the UNMASKED mesh numbering for all fields.
+static int ellipticOgsBlock(mesh_t* mesh, const std::vector<int>& EToB, elliptic_t* elliptic)
+{
+  const int largeNumber = 1 << 20;
+  const dlong Nlocal = mesh->Nlocal;
+  const int Nfields = elliptic->Nfields;
+  const dlong offset = elliptic->fieldOffset;
+  NRSB_REQUIRE(EToB.size() >= (size_t)Nfields * mesh->Nelements * 6, "EToB needs Nfields * Nelements * 6 entries");
+  std::vector<std::vector<int>> fn;
+  face_nodes(mesh->N, fn);
+  std::vector<char> isMasked((size_t)Nfields * Nlocal, 0);
+  int rc;
+  for (int fld = 0; fld < Nfields; ++fld) {
+    std::vector<double> mapB(Nlocal, (double)largeNumber);
+    for (dlong e = 0; e < mesh->Nelements; ++e)
+      for (int f = 0; f < 6; ++f) {
+        const int bc = EToB[f + (size_t)e * 6 + (size_t)fld * mesh->Nelements * 6];
+        if (bc > 0)
+          for (int n : fn[f]) {
+            double& m = mapB[n + (size_t)e * mesh->Np];
+            m = std::min((double)bc, m);
+          }
+      }
+    dbuf<double> d;
+    if ((rc = d.upload(mapB))) return rc;
+    if ((rc = mesh->oogs->startFinish<double>(d.p, 1, 0, gs_op::min, 0, nullptr, nullptr))) return rc;
+    NRSB_CUDA(cudaDeviceSynchronize());
+    if ((rc = d.download(mapB))) return rc;
+    for (dlong n = 0; n < Nlocal; ++n) isMasked[(size_t)fld * Nlocal + n] = mapB[n] == 1.0;  // DIRICHLET
+  }
+  elliptic->maskIds.clear();
+  std::vector<dlong> loc, glo;
+  for (int fld = 0; fld < Nfields; ++fld) {
+    for (dlong n = 0; n < Nlocal; ++n)
+      if (isMasked[(size_t)fld * Nlocal + n]) elliptic->maskIds.push_back(n + fld * offset);
+    for (dlong e : mesh->localGatherElementList)
+      for (int q = 0; q < mesh->Np; ++q)
+        if (isMasked[(size_t)fld * Nlocal + (size_t)e * mesh->Np + q]) loc.push_back(e * mesh->Np + q + fld * offset);
+    for (dlong e : mesh->globalGatherElementList)
+      for (int q = 0; q < mesh->Np; ++q)
+        if (isMasked[(size_t)fld * Nlocal + (size_t)e * mesh->Np + q]) glo.push_back(e * mesh->Np + q + fld * offset);
+  }
+  elliptic->Nmasked = (dlong)elliptic->maskIds.size();
+  elliptic->NmaskedLocal = (dlong)loc.size();
+  elliptic->NmaskedGlobal = (dlong)glo.size();
+  if ((rc = elliptic->o_maskIds.upload(elliptic->maskIds))) return rc;
+  if ((rc = elliptic->o_maskIdsLocal.upload(loc))) return rc;
+  if ((rc = elliptic->o_maskIdsGlobal.upload(glo))) return rc;
+  elliptic->ogs.reset(new ogs_t());
+  if ((rc = elliptic->ogs->setup(Nlocal, mesh->globalIds.data(), mesh->topo.nranks > 1 ? &mesh->topo : nullptr)))
+    return rc;
+  elliptic->oogs.reset(new oogs_t());
+  if ((rc = elliptic->oogs->setup(elliptic->ogs.get(), mesh->comm, Nfields))) return rc;
+  elliptic->o_invDegree = elliptic->ogs->d_invDegree;
+  elliptic->o_invDegreePfloat = elliptic->ogs->d_invDegreePfloat;
+  // weights of the block inner products: invDegree per field, zero in the padding between Nlocal and fieldOffset
+  std::vector<double> w((size_t)Nfields * offset, 0.0);
+  for (int fld = 0; fld < Nfields; ++fld)
+    for (dlong n = 0; n < Nlocal; ++n) w[(size_t)fld * offset + n] = elliptic->ogs->invDegree[n];
+  return elliptic->o_weightBlock.upload(w);
+}
+
 int ellipticOgs(mesh_t* mesh, const std::vector<int>& EToB, elliptic_t* elliptic)
 {
+  if (elliptic->Nfields > 1) return ellipticOgsBlock(mesh, EToB, elliptic);
   const int largeNumber = 1 << 20;
   const dlong Nlocal = mesh->Nlocal;
   std::vector<std::vector<int>> fn;
@@ -153,12 +217,39 @@ struct prec_traits<float> {
   static constexpr int idx = 1;
 };
 
+// block solver: ellipticBlockPartialAxCoeffHex3D / ellipticStressPartialAxCoeffHex3D (ellipticSetup.cpp:240-249)
+static int ellipticAxBlock(elliptic_t* elliptic, dlong NelementsList, const dlong* o_elementList, const double* o_q,
+                           double* o_Aq)
+{
+  mesh_t* mesh = elliptic->mesh;
+  const double* l0 = elliptic->lambdaField ? elliptic->o_lambda0Field : elliptic->o_lambda0.p;
+  const double* l1 = elliptic->lambdaField ? elliptic->o_lambda1Field : elliptic->o_lambda1.p;
+  if (elliptic->stressForm) {
+    NRSB_REQUIRE(mesh->o_vgeo.p != nullptr, "stress form needs mesh->o_vgeo");
+    return ax_stress_launch<double>(mesh->Nq, NelementsList, elliptic->fieldOffset, elliptic->loffset, o_elementList,
+                                    mesh->o_vgeo.p, mesh->D.data(), l0, l1, elliptic->lambdaField ? 1 : 0, o_q, o_Aq,
+                                    elliptic->stream);
+  }
+  NRSB_REQUIRE(mesh->o_ggeo.p != nullptr, "fp64 geometric factors are not resident");
+  return ax_block_launch<double>(mesh->Nq, 1, NelementsList, elliptic->Nfields, elliptic->fieldOffset,
+                                 elliptic->loffset, o_elementList, mesh->o_ggeo.p, mesh->D.data(), l0, l1,
+                                 elliptic->lambdaField ? 1 : 0, o_q, o_Aq, elliptic->stream);
+}
+template <typename T>
+static int ellipticAxBlockT(elliptic_t* elliptic, dlong n, const dlong* list, const T* o_q, T* o_Aq)
+{
+  if constexpr (sizeof(T) == 8) return ellipticAxBlock(elliptic, n, list, o_q, o_Aq);
+  set_last_error("block solves run in fp64");
+  return NRSB_ERR_INVALID;
+}
+
 template <typename T>
 static int ellipticAxDot(elliptic_t* elliptic, dlong NelementsList, const dlong* o_elementList, const T* o_q, T* o_Aq,
                          AxDot* dot)
 {
   if (dot) dot->n = 0;
   if (NelementsList == 0) return NRSB_OK;
+  if (elliptic->Nfields > 1) return ellipticAxBlockT<T>(elliptic, NelementsList, o_elementList, o_q, o_Aq);
   mesh_t* mesh = elliptic->mesh;
   using P = prec_traits<T>;
   NRSB_REQUIRE(P::ggeo(mesh) != nullptr, "geometric factors of the requested precision are not resident");
@@ -173,6 +264,7 @@ template <typename T>
 int ellipticAx(elliptic_t* elliptic, dlong NelementsList, const dlong* o_elementList, const T* o_q, T* o_Aq)
 {
   if (NelementsList == 0) return NRSB_OK;
+  if (elliptic->Nfields > 1) return ellipticAxBlockT<T>(elliptic, NelementsList, o_elementList, o_q, o_Aq);
   mesh_t* mesh = elliptic->mesh;
   using P = prec_traits<T>;
   NRSB_REQUIRE(P::ggeo(mesh) != nullptr, "geometric factors of the requested precision are not resident");
@@ -204,6 +296,14 @@ int ellipticOperator(elliptic_t* elliptic, const T* o_q, T* o_Aq, bool masked, A
   oogs_t* oogs = elliptic->oogs.get();
   int rc;
   const dlong nm = masked ? elliptic->Nmasked : 0;
+  if (elliptic->Nfields > 1) {
+    // block solver: the handle carries the UNMASKED numbering (ellipticOgs.cpp:121-131 builds a masked handle for one
+    // field only), so masked nodes belong to rows: zero them first, then sum (all copies of a Dirichlet node are masked)
+    if ((rc = ellipticAx<T>(elliptic, mesh->Nelements, mesh->o_elementList.p, o_q, o_Aq))) return rc;
+    if (nm)
+      if ((rc = mask_launch<T>(nm, elliptic->o_maskIds.p, o_Aq, elliptic->stream))) return rc;
+    return oogs->startFinish<T>(o_Aq, elliptic->Nfields, elliptic->fieldOffset, gs_op::add, 0, nullptr, elliptic->stream);
+  }
   using P = prec_traits<T>;
   const int axv = elliptic->ax_variant[P::idx] < 0 ? ax_default_variant(mesh->Nq, (int)sizeof(T))
                                                    : elliptic->ax_variant[P::idx];
@@ -571,7 +671,18 @@ int ellipticSolveSetup(elliptic_t* elliptic)
   options_t& options = elliptic->options;
   NRSB_REQUIRE(!elliptic->name.empty(), "Empty elliptic solver name!");
   options.setArgs("DISCRETIZATION", "CONTINUOUS");
-  NRSB_REQUIRE(elliptic->Nfields == 1, "block (Nfields > 1) solves are a 'next' row (SURVEY N3)");
+  NRSB_REQUIRE(elliptic->Nfields >= 1 && elliptic->Nfields <= 3, "Invalid Nfields");  // ellipticSetup.cpp:81-86
+  if (elliptic->Nfields > 1) {
+    // block solver (ellipticSetup.cpp:53-57,131): Jacobi or no preconditioner, PCG, Helmholtz form, fp64
+    NRSB_REQUIRE(!options.compareArgs("PRECONDITIONER", "MULTIGRID"),
+                 "Block solver is implemented for C0-HEXES with Jacobi preconditioner only");
+    NRSB_REQUIRE(options.compareArgs("SOLVER", "PCG"), "block solves use PCG");
+    NRSB_REQUIRE(!options.compareArgs("INITIAL GUESS", "PROJECTION"), "block solves: no solution projection yet");
+    NRSB_REQUIRE(elliptic->Nfields == 3, "block kernels are built for three fields");
+    elliptic->poisson = false;
+    if (elliptic->stressForm)
+      if (int rcv = mesh->ensure_vgeo()) return rcv;
+  }
   // fieldOffset: Nlocal rounded up to ALIGN_SIZE bytes (setup.cpp:295-299, nrssys.hpp:122)
   if (elliptic->fieldOffset == 0) {
     const dlong per = 1024 / sizeof(double);
@@ -587,6 +698,16 @@ int ellipticSolveSetup(elliptic_t* elliptic)
   if ((rc = elliptic->o_rPfloat.alloc(fo))) return rc;
   if ((rc = elliptic->o_zPfloat.alloc(fo))) return rc;
   std::vector<double> l0(1, elliptic->lambda0Value), l1(1, elliptic->lambda1Value);
+  if (elliptic->Nfields > 1) {
+    // one constant per field, read by the block kernels at lambda[fld * loffset] with loffset = 1
+    l0.assign(elliptic->Nfields, elliptic->lambda0Value);
+    l1.assign(elliptic->Nfields, elliptic->lambda1Value);
+    if (!elliptic->blockLambda0.empty()) l0 = elliptic->blockLambda0;
+    if (!elliptic->blockLambda1.empty()) l1 = elliptic->blockLambda1;
+    NRSB_REQUIRE((int)l0.size() == elliptic->Nfields && (int)l1.size() == elliptic->Nfields,
+                 "block coefficients: one value per field");
+    if (!elliptic->lambdaField) elliptic->loffset = 1;
+  }
   if ((rc = elliptic->o_lambda0.upload(l0))) return rc;
   if ((rc = elliptic->o_lambda1.upload(l1))) return rc;
   std::vector<float> l0f(1, (float)elliptic->lambda0Value), l1f(1, (float)elliptic->lambda1Value);
@@ -676,7 +797,7 @@ int ellipticPreconditioner(elliptic_t* elliptic, double* o_r, double* o_z)
   const long Nall = (long)elliptic->fieldOffset * elliptic->Nfields;
   int rc;
   if (options.compareArgs("PRECONDITIONER", "JACOBI")) {
-    if ((rc = axmyz_launch<double>(mesh->Nlocal, 1.0, o_r, precon->o_invDiagA.p, o_z, elliptic->stream))) return rc;
+    if ((rc = axmyz_launch<double>(elliptic->Nvec(), 1.0, o_r, precon->o_invDiagA.p, o_z, elliptic->stream))) return rc;
   } else if (options.compareArgs("PRECONDITIONER", "MULTIGRID")) {
     // pfill(z)=0 ; cast r ; V-cycle ; cast z  (ellipticPreconditioner.cpp:57-62)
     if ((rc = fill_launch<float>(Nall, 0.f, elliptic->o_zPfloat.p, elliptic->stream))) return rc;
@@ -707,8 +828,8 @@ int pcg(elliptic_t* elliptic, double* o_r, double* o_x, double tol, int MAXIT, d
   double* o_p = elliptic->o_p.p;
   double* o_z = precond ? elliptic->o_z.p : o_r;
   double* o_Ap = elliptic->o_Ap.p;
-  const double* o_weight = elliptic->o_invDegree;
-  const long N = mesh->Nlocal;
+  const double* o_weight = elliptic->o_weight();
+  const long N = elliptic->Nvec();
   int rc;
   if ((rc = fill_launch<double>((long)elliptic->fieldOffset * elliptic->Nfields, 0.0, o_p, st))) return rc;
 
@@ -940,7 +1061,7 @@ int pgmres(elliptic_t* elliptic, double* o_r, double* o_x, double tol, int MAXIT
 // ------------------------------------------------------------------------------------------
 static int weighted_norm(elliptic_t* elliptic, const double* o_v, double* out)
 {
-  int rc = wnorm2_launch<double>(elliptic->mesh->Nlocal, elliptic->o_invDegree, o_v, elliptic->o_scal.p + S_NORM,
+  int rc = wnorm2_launch<double>(elliptic->Nvec(), elliptic->o_weight(), o_v, elliptic->o_scal.p + S_NORM,
                                  elliptic->ws, elliptic->stream);
   if (rc) return rc;
   double v;
@@ -954,7 +1075,7 @@ int ellipticSolve(elliptic_t* elliptic, double* o_r, double* o_x)
   options_t& options = elliptic->options;
   mesh_t* mesh = elliptic->mesh;
   cudaStream_t st = elliptic->stream;
-  const long N = mesh->Nlocal;
+  const long N = elliptic->Nvec();
   const long fo = (long)elliptic->fieldOffset * elliptic->Nfields;
   int maxIter = 999;
   options.getArgs("MAXIMUM ITERATIONS", maxIter);
@@ -976,7 +1097,7 @@ int ellipticSolve(elliptic_t* elliptic, double* o_r, double* o_x)
   if (elliptic->allNeumann)
     if ((rc = ellipticZeroMean(elliptic, o_r))) return rc;
   // mask + gather-scatter of the residual
-  if (elliptic->oogs->ogs->NhaloGather) {
+  if (elliptic->oogs->ogs->NhaloGather || elliptic->Nfields > 1) {  // (block solver: unmasked numbering)
     if ((rc = ellipticApplyMask<double>(elliptic, o_r))) return rc;
     if ((rc = elliptic->oogs->startFinish<double>(o_r, elliptic->Nfields, elliptic->fieldOffset, gs_op::add, 0, nullptr,
                                                   st)))

@@ -164,6 +164,8 @@ class mesh_t {
   // device
   dbuf<double> o_ggeo;
   dbuf<float> o_ggeoPfloat;
+  dbuf<double> o_vgeo;  // [E][12][Np] rx..tz, J, JW, 1/JW (mesh3D.h:82-93): built on demand (stress-form block solves)
+  int ensure_vgeo();
   dbuf<dlong> o_elementList, o_globalGatherElementList, o_localGatherElementList;
   dbuf<dlong> o_haloFirstElementList;  // globalGather elements followed by localGather elements
   dlong NglobalGatherElements = 0, NlocalGatherElements = 0;
@@ -338,6 +340,15 @@ class elliptic_t {
   // variable coefficients (ELLIPTIC COEFF FIELD, p_lambda = 1): per-node lambda0 / lambda1.  The fp64 fields of the
   // solver belong to the caller (like the reference's o_lambda0 / o_lambda1 handles); the fp32 copies -- level 0 a
   // cast, coarser levels interpolated -- are refreshed by ellipticMultiGridUpdateLambda.
+  // block solver (Nfields > 1; ellipticSetup.cpp:81-131,209-249): the unmasked mesh numbering serves all fields, the
+  // Dirichlet mask is per field (ids n + fld * fieldOffset), the operator is the block Helmholtz or, with stressForm,
+  // the coupled stress operator.  Constant coefficients: one value per field, loffset = 1.
+  bool stressForm = false;
+  std::vector<double> blockLambda0, blockLambda1;  // per-field constants given at setup (empty: lambda0/1Value)
+  dbuf<double> o_weightBlock;                      // invDegree replicated per field, zero in the padding
+  // vector length and weights of every reduction / streaming op of the Krylov loop
+  long Nvec() const { return Nfields == 1 ? (long)mesh->Nlocal : (long)Nfields * fieldOffset; }
+  const double* o_weight() const { return Nfields == 1 ? o_invDegree : o_weightBlock.p; }
   bool lambdaField = false;
   const double* o_lambda0Field = nullptr;
   const double* o_lambda1Field = nullptr;

@@ -57,6 +57,6 @@ int build_diagonal_launch(int Nq, dlong Nelements, int Nfields, dlong offset, dl
 bool transfer_supported(int NqF, int NqC);
 bool fdm_supported(int Nq);  // extended size Nq + 2 instantiated
 int geometric_factors_launch(int Nq, dlong Nelements, const double* d_D, const double* d_gllw, const double* x,
-                             const double* y, const double* z, double* ggeo, double* Jac, cudaStream_t stream);
+                             const double* y, const double* z, double* ggeo, double* Jac, cudaStream_t stream, double* vgeo = nullptr);
 
 }  // namespace nrsb

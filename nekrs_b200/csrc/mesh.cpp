@@ -187,6 +187,20 @@ void mesh_t::interp_matrix(const std::vector<double>& zin, const std::vector<dou
   }
 }
 
+int mesh_t::ensure_vgeo()
+{
+  if (o_vgeo.p || Nlocal == 0) return NRSB_OK;
+  int rc;
+  dbuf<double> dx, dy, dz, dD, dw;
+  if ((rc = dx.upload(x)) || (rc = dy.upload(y)) || (rc = dz.upload(z)) || (rc = dD.upload(D)) || (rc = dw.upload(gllw)))
+    return rc;
+  if ((rc = o_vgeo.alloc((size_t)Nlocal * 12, false))) return rc;
+  if ((rc = geometric_factors_launch(Nq, Nelements, dD.p, dw.p, dx.p, dy.p, dz.p, nullptr, nullptr, nullptr, o_vgeo.p)))
+    return rc;
+  NRSB_CUDA(cudaDeviceSynchronize());
+  return NRSB_OK;
+}
+
 int mesh_t::setup(int N_, dlong Nelements_, const double* x_, const double* y_, const double* z_,
                   const hlong* globalIds_, const int* EToB_, comm_t* comm_, const SharedTopology* topo_,
                   bool keepFp64Geo)

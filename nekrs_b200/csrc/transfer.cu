@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(256)
     geometric_factors_kernel(const dlong Nelements, const int Nq, const double* __restrict__ D,
                              const double* __restrict__ gllw, const double* __restrict__ x,
                              const double* __restrict__ y, const double* __restrict__ z, double* __restrict__ ggeo,
-                             double* __restrict__ Jac)
+                             double* __restrict__ Jac, double* __restrict__ vgeo)
 {
   const int Np = Nq * Nq * Nq;
   const long gid = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -215,8 +215,14 @@ __global__ void __launch_bounds__(256)
   const double rx = (ys * zt - zs * yt) * Jinv, ry = -(xs * zt - zs * xt) * Jinv, rz = (xs * yt - ys * xt) * Jinv;
   const double sx = -(yr * zt - zr * yt) * Jinv, sy = (xr * zt - zr * xt) * Jinv, sz = -(xr * yt - yr * xt) * Jinv;
   const double tx = (yr * zs - zr * ys) * Jinv, ty = -(xr * zs - zr * xs) * Jinv, tz = (xr * ys - yr * xs) * Jinv;
-  double* g = ggeo + (size_t)7 * Np * e + n;
   if (Jac) Jac[(size_t)e * Np + n] = J;
+  if (vgeo) {  // mesh->vgeo: rx,ry,rz,sx,sy,sz,tx,ty,tz,J,JW,1/JW (mesh3D.h:82-93, meshGeometricFactorsHex3D.cpp)
+    double* v = vgeo + (size_t)12 * Np * e + n;
+    const double f[12] = {rx, ry, rz, sx, sy, sz, tx, ty, tz, J, JW, 1. / JW};
+    for (int c = 0; c < 12; ++c) v[c * (size_t)Np] = f[c];
+  }
+  if (!ggeo) return;
+  double* g = ggeo + (size_t)7 * Np * e + n;
   g[0 * (size_t)Np] = JW * (rx * rx + ry * ry + rz * rz);
   g[1 * (size_t)Np] = JW * (rx * sx + ry * sy + rz * sz);
   g[4 * (size_t)Np] = JW * (rx * tx + ry * ty + rz * tz);
@@ -227,12 +233,13 @@ __global__ void __launch_bounds__(256)
 }
 
 int geometric_factors_launch(int Nq, dlong Nelements, const double* d_D, const double* d_gllw, const double* x,
-                             const double* y, const double* z, double* ggeo, double* Jac, cudaStream_t stream)
+                             const double* y, const double* z, double* ggeo, double* Jac, cudaStream_t stream,
+                             double* vgeo)
 {
   const long total = (long)Nelements * Nq * Nq * Nq;
   if (total == 0) return NRSB_OK;
   geometric_factors_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(Nelements, Nq, d_D, d_gllw, x, y, z,
-                                                                                ggeo, Jac);
+                                                                                ggeo, Jac, vgeo);
   NRSB_CHECK_LAUNCH();
   return NRSB_OK;
 }

@@ -22,7 +22,8 @@ class _Config(C.Structure):
                 ("globalIds", C.c_void_p), ("EToB", C.c_void_p), ("topo", C.c_void_p), ("nLevels", C.c_int),
                 ("levelOrders", C.c_void_p), ("levelGlobalIds", C.c_void_p), ("levelTopo", C.c_void_p),
                 ("options", C.c_char_p), ("poisson", C.c_int), ("lambda0", C.c_double), ("lambda1", C.c_double),
-                ("comm", C.c_void_p), ("name", C.c_char_p)]
+                ("comm", C.c_void_p), ("name", C.c_char_p), ("Nfields", C.c_int), ("stressForm", C.c_int),
+                ("blockLambda0", C.c_void_p), ("blockLambda1", C.c_void_p)]
 
 
 class Topology:
@@ -79,8 +80,11 @@ class Elliptic:
     """elliptic_t handle."""
 
     def __init__(self, mesh: meshgen.HexMesh, options: dict, *, comm=None, topo_of=None, poisson=True, lambda0=1.0,
-                 lambda1=0.0, name="pressure"):
+                 lambda1=0.0, name="pressure", Nfields=1, stress_form=False, EToB=None, block_lambda0=None,
+                 block_lambda1=None):
+        """Nfields = 3: block solver (velocity): EToB [Nfields][Nelements][6], one lambda0 / lambda1 per field."""
         self.mesh = mesh
+        self.Nfields = Nfields
         self.options = dict(options)
         self.N, self.Np = mesh.N, mesh.Np
         self.Nlocal = mesh.Nelements * mesh.Np
@@ -97,15 +101,21 @@ class Elliptic:
         topo_ptrs = (C.c_void_p * max(len(levels), 1))(*[C.addressof(t.c) for t in lvl_topos]) if lvl_topos else None
         x, y, z = (np.ascontiguousarray(a, dtype=np.float64) for a in (mesh.x, mesh.y, mesh.z))
         gid = np.ascontiguousarray(mesh.global_ids, dtype=np.int64)
-        etob = np.ascontiguousarray(mesh.EToB, dtype=np.int32)
-        self._keep += [x, y, z, gid, etob, orders, lvl_ids, id_ptrs, topo, lvl_topos, topo_ptrs, opt_txt]
+        etob = np.ascontiguousarray(mesh.EToB if EToB is None else EToB, dtype=np.int32).ravel()
+        if Nfields > 1 and etob.size == mesh.Nelements * 6:
+            etob = np.ascontiguousarray(np.tile(etob, Nfields))
+        assert etob.size == max(Nfields, 1) * mesh.Nelements * 6
+        bl0 = None if block_lambda0 is None else np.ascontiguousarray(block_lambda0, dtype=np.float64)
+        bl1 = None if block_lambda1 is None else np.ascontiguousarray(block_lambda1, dtype=np.float64)
+        self._keep += [x, y, z, gid, etob, orders, lvl_ids, id_ptrs, topo, lvl_topos, topo_ptrs, opt_txt, bl0, bl1]
         cfg = _Config(mesh.N, mesh.Nelements, x.ctypes.data, y.ctypes.data, z.ctypes.data, gid.ctypes.data,
                       etob.ctypes.data, C.addressof(topo.c) if topo else None, len(levels),
                       orders.ctypes.data if len(levels) else None,
                       C.cast(id_ptrs, C.c_void_p) if len(levels) else None,
                       C.cast(topo_ptrs, C.c_void_p) if topo_ptrs is not None else None, opt_txt,
                       1 if poisson else 0, lambda0, lambda1, comm.handle if comm is not None else None,
-                      name.encode())
+                      name.encode(), Nfields, 1 if stress_form else 0,
+                      bl0.ctypes.data if bl0 is not None else None, bl1.ctypes.data if bl1 is not None else None)
         self._h = C.c_void_p()
         call("nrsb_elliptic_setup", C.byref(cfg), C.byref(self._h))
         self.fieldOffset = self.get_int("fieldOffset")

@@ -90,11 +90,14 @@ class OElliptic:
     def apply_mask(self, v):
         self.orc.mask(self.mask_ids, v)
 
+    def gs(self, v):
+        self.orc.gs_add(self.ogs, v)
+
     def operator(self, q, Aq, masked=True):
         self.ax(q, Aq)
         if masked:
             self.apply_mask(Aq)
-        self.orc.gs_add(self.ogs, Aq)
+        self.gs(Aq)
 
     def build_inv_diag(self, dtype):
         """ellipticBlockBuildDiagonalHex3D.okl + gs + 1/x (ellipticUpdateJacobi.cpp:32-85)."""
@@ -591,6 +594,7 @@ class OSolver:
         m = OMesh(self.orc, hexmesh.N, hexmesh.Nelements, hexmesh.x, hexmesh.y, hexmesh.z, hexmesh.global_ids,
                   hexmesh.EToB)
         self.mesh = m
+        self.nvec = m.Nlocal
         self.ell = OElliptic(self.orc, m, o, poisson=poisson, lambda0=lambda0, lambda1=lambda1)
         if not poisson or lambda0 != 1.0:
             assert not compare(o, "PRECONDITIONER", "MULTIGRID"), "the multigrid restatement is Poisson-only"
@@ -687,7 +691,7 @@ class OSolver:
             self.coarse.solve(rhs, x)
 
     def preconditioner(self, r, z):
-        o, orc, n = self.options, self.orc, self.mesh.Nlocal
+        o, orc, n = self.options, self.orc, self.nvec
         if compare(o, "PRECONDITIONER", "JACOBI"):
             orc.axmyz(n, 1.0, r, self.inv_diag, z)
         elif compare(o, "PRECONDITIONER", "MULTIGRID"):
@@ -712,13 +716,13 @@ class OSolver:
         q[:n] += -mean
 
     def wnorm(self, v):
-        n = self.mesh.Nlocal
+        n = self.nvec
         return np.sqrt(self.orc.weighted_norm2_sq(n, self.ell.inv_degree, v)) * np.sqrt(self.resNormFactor)
 
     # ---- ellipticSolve
     def solve(self, rhs, x):
         o, orc, ell = self.options, self.orc, self.ell
-        n = self.mesh.Nlocal
+        n = self.nvec
         r = np.ascontiguousarray(rhs, dtype=np.float64).copy()
         x = np.ascontiguousarray(x, dtype=np.float64)
         maxIter = int(o.get("MAXIMUM ITERATIONS", 999))
@@ -730,7 +734,7 @@ class OSolver:
         if ell.allNeumann:
             self.zero_mean(r)
         ell.apply_mask(r)
-        orc.gs_add(ell.ogs, r)
+        ell.gs(r)
         x0 = x.copy()
         x[:] = 0
         if self.proj is not None:
@@ -756,7 +760,7 @@ class OSolver:
 
     def pcg(self, r, x, tol, MAXIT):
         o, orc, ell = self.options, self.orc, self.ell
-        n = self.mesh.Nlocal
+        n = self.nvec
         flexible = compare(o, "SOLVER", "FLEXIBLE")
         precond = not compare(o, "PRECONDITIONER", "NONE")
         p, Ap = np.zeros(n), np.zeros(n)
@@ -955,3 +959,109 @@ class Projection:
             self.xx[:n] = x[:n]
             self.matvec(0, 0)
             self.update_space()
+
+# ------------------------------------------------------------------------------------------ block solver
+class OBlockElliptic:
+    """elliptic_t with Nfields = 3 (ellipticSetup.cpp:81-131,192-249; ellipticOgs.cpp:17-131): boundary flags and mask
+    per field, the UNMASKED mesh numbering for the gather-scatter of all fields, block Helmholtz or stress operator."""
+
+    def __init__(self, orc: Orc, mesh: OMesh, EToB, lambda0, lambda1, offset, stress_form):
+        self.orc, self.mesh, self.offset, self.stress = orc, mesh, offset, bool(stress_form)
+        self.Nfields = 3
+        etob = np.asarray(EToB, dtype=np.int32).reshape(self.Nfields, mesh.E * 6)
+        ids = []
+        for f in range(self.Nfields):
+            mi, _ = sem.dirichlet_mask_ids(mesh.N, mesh.E, etob[f], mesh.ogs, orc)
+            ids.append(np.asarray(mi, dtype=np.int64) + f * offset)
+        self.mask_ids = np.concatenate(ids).astype(np.int32)
+        self.ogs = mesh.ogs
+        self.allNeumann = 0
+        w = np.zeros(self.Nfields * offset)
+        for f in range(self.Nfields):
+            w[f * offset:f * offset + mesh.Nlocal] = mesh.ogs.inv_degree
+        self.inv_degree = w
+        # one constant per field, read at lambda[fld * loffset] with loffset = 1
+        self.lam0 = np.ascontiguousarray(lambda0, dtype=np.float64)
+        self.lam1 = np.ascontiguousarray(lambda1, dtype=np.float64)
+        if self.stress:
+            self.vgeo = volume_factors(mesh)
+
+    def ax(self, q, Aq):
+        m = self.mesh
+        if self.stress:
+            self.orc.ax_stress(m.N, m.element_list, self.vgeo, m.D, q, Aq, self.lam0, self.lam1, self.offset, 1)
+        else:
+            self.orc.ax_block(m.N, m.element_list, m.ggeo, m.D, q, Aq, self.lam0, self.lam1, self.offset, 1)
+
+    def apply_mask(self, v):
+        self.orc.mask(self.mask_ids, v)
+
+    def gs(self, v):
+        self.orc.gs_add(self.ogs, v, k=self.Nfields, stride=self.offset)
+
+    def operator(self, q, Aq, masked=True):
+        self.ax(q, Aq)
+        if masked:
+            self.apply_mask(Aq)
+        self.gs(Aq)
+
+    def build_inv_diag(self):
+        """ellipticBlockBuildDiagonalHex3D per field (also in stress form: ellipticUpdateJacobi.cpp:38-47), gs, 1/x."""
+        from . import kernels as K
+        m = self.mesh
+        out = np.zeros(self.Nfields * self.offset)
+        g = m.ggeo.reshape(m.E, 7, m.Np)
+        for f in range(self.Nfields):
+            d = K.build_diagonal(m.N, m.E, g, m.D, np.array([self.lam0[f]]), np.array([self.lam1[f]]), poisson=False,
+                                 lambda_field=False)
+            out[f * self.offset:f * self.offset + m.Nlocal] = d
+        self.gs(out)
+        inv = np.zeros_like(out)
+        for f in range(self.Nfields):
+            sl = slice(f * self.offset, f * self.offset + m.Nlocal)
+            inv[sl] = 1.0 / out[sl]
+        return inv
+
+
+def volume_factors(m: OMesh):
+    """mesh->vgeo (meshGeometricFactorsHex3D.cpp; ids mesh3D.h:82-93): [E][12][Np] = rx,ry,rz,sx,sy,sz,tx,ty,tz,J,JW,1/JW."""
+    E, Nq, Np, D = m.E, m.Nq, m.Np, m.D
+    X = [a.reshape(E, Nq, Nq, Nq) for a in (m.x, m.y, m.z)]
+    J = np.empty((E, Nq, Nq, Nq, 3, 3))
+    for a, f in enumerate(X):
+        J[..., a, 0] = np.einsum("im,ekjm->ekji", D, f)
+        J[..., a, 1] = np.einsum("jm,ekmi->ekji", D, f)
+        J[..., a, 2] = np.einsum("km,emji->ekji", D, f)
+    Ji = np.linalg.inv(J)  # rows r,s,t ; columns x,y,z
+    det = np.linalg.det(J)
+    w = m.gllw
+    W = (w[:, None, None] * w[None, :, None] * w[None, None, :]).reshape(1, Np)
+    v = np.zeros((E, 12, Np))
+    for a in range(3):
+        for b in range(3):
+            v[:, 3 * a + b] = Ji[..., a, b].reshape(E, Np)
+    v[:, 9] = det.reshape(E, Np)
+    v[:, 10] = det.reshape(E, Np) * W
+    v[:, 11] = 1.0 / v[:, 10]
+    return v
+
+
+class OBlockSolver(OSolver):
+    """ellipticSolveSetup + ellipticSolve for a block (velocity-type) solve: Jacobi or no preconditioner, PCG."""
+
+    def __init__(self, hexmesh, options: dict, EToB, lambda0, lambda1, orc: Orc = None, stress_form=False):
+        self.orc = orc or Orc()
+        self.options = {k.upper(): str(v).upper() for k, v in options.items()}
+        self.hex = hexmesh
+        o = self.options
+        assert compare(o, "SOLVER", "PCG") and not compare(o, "PRECONDITIONER", "MULTIGRID")
+        m = OMesh(self.orc, hexmesh.N, hexmesh.Nelements, hexmesh.x, hexmesh.y, hexmesh.z, hexmesh.global_ids,
+                  np.asarray(EToB).reshape(3, -1)[0])
+        self.mesh = m
+        per = 1024 // 8
+        self.fieldOffset = ((m.Nlocal + per - 1) // per) * per
+        self.nvec = 3 * self.fieldOffset
+        self.ell = OBlockElliptic(self.orc, m, EToB, lambda0, lambda1, self.fieldOffset, stress_form)
+        self.levels, self.res_history, self.Niter, self.proj = [], [], 0, None
+        if compare(o, "PRECONDITIONER", "JACOBI"):
+            self.inv_diag = self.ell.build_inv_diag()

@@ -148,6 +148,40 @@ def main():
     report("BP5 PCG residual history", it == ref.Niter and np.max(np.abs(h - hr) / hr) < 1e-12,
            "its %d/%d maxrel %.2e" % (it, ref.Niter, np.max(np.abs(h - hr) / hr)))
 
+    # ---- block solver (Nfields = 3, stress form, Jacobi-PCG): three-field exchange, per-field masks, block reductions
+    if not light:
+        lam0b, lam1b = [1.0, 1.3, 0.8], [0.6, 0.5, 0.9]
+        opts_b = {"SOLVER": "PCG", "PRECONDITIONER": "JACOBI", "MAXIMUM ITERATIONS": "400", "SOLVER TOLERANCE": "1e-9",
+                  "LINEAR SOLVER STOPPING CRITERION": "RELATIVE"}
+        ell_b = Elliptic(part, opts_b, comm=comm, topo_of=topo_of, poisson=False, Nfields=3, stress_form=True,
+                         block_lambda0=lam0b, block_lambda1=lam1b, name="velocity")
+        ref_b = driver.OBlockSolver(whole, opts_b, np.tile(np.asarray(whole.EToB), 3), lam0b, lam1b, orc,
+                                    stress_form=True)
+        offW, offP = ref_b.fieldOffset, ell_b.fieldOffset
+        nW = whole.Nelements * Np
+        rb = np.random.Generator(np.random.PCG64(11))
+        qW = np.zeros(3 * offW)
+        for f in range(3):
+            qW[f * offW:f * offW + nW] = rb.random(nW)
+        outW = np.zeros(3 * offW)
+        ref_b.ell.operator(qW, outW)
+        to_part = lambda v: np.concatenate([np.r_[v[f * offW + gnode], np.zeros(offP - nloc)] for f in range(3)])
+        d_qb, d_Aqb = DB(like=to_part(qW)), DB.zeros(3 * offP, np.float64)
+        for rep in range(3):
+            ell_b.operator(d_qb, d_Aqb)
+        eb = np.max(np.abs(d_Aqb.download() - to_part(outW))) / np.max(np.abs(outW))
+        report("block stress operator vs oracle", eb < 1e-12, "relerr %.2e" % eb)
+        rhsW = np.zeros(3 * offW)
+        for f in range(3):
+            rhsW[f * offW:f * offW + nW] = (f + 1) * rhs_glob
+        xW = ref_b.solve(rhsW, np.zeros(3 * offW))
+        d_xb = DB.zeros(3 * offP, np.float64)
+        itb = ell_b.solve(DB(like=to_part(rhsW)), d_xb)
+        exb = np.max(np.abs(d_xb.download() - to_part(xW))) / np.max(np.abs(xW))
+        report("block Jacobi-PCG", abs(itb - ref_b.Niter) <= 1 and exb < 1e-7,
+               "its %d/%d relerr %.2e" % (itb, ref_b.Niter, exb))
+        ell_b.destroy()
+
     # ---- BPS5: p-multigrid preconditioned FGMRES
     for smoother in (() if light else ("FOURTHOPTCHEBYSHEV+RAS", "FOURTHOPTCHEBYSHEV+ASM")):
         opts = pressure_options(**{"MULTIGRID SMOOTHER": smoother})
