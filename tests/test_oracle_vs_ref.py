@@ -282,3 +282,50 @@ def test_stress_ax_symmetric_and_rigid_motions(orc):
     Ar = np.zeros(3 * offset)
     orc.ax_stress(N, el, vgeo, D, rot, Ar, lam0, lam1, offset, loffset)
     assert np.max(np.abs(Ar)) < 1e-10 * np.max(np.abs(A1))
+
+
+@pytest.mark.parametrize("stress", [False, True])
+def test_oracle_block_solver(orc, stress):
+    """The oracle's block solver (OBlockSolver: per-field masks over the unmasked numbering, block / stress operator,
+    Jacobi-PCG): the converged solution satisfies the masked, assembled system, and the per-field Jacobi diagonal is the
+    probed diagonal of the assembled block operator."""
+    from nekrs_b200 import meshgen
+    from oracle import driver
+    mesh = meshgen.box_mesh(3, (2, 2, 2), kershaw_eps=0.3)
+    E, Np = mesh.Nelements, mesh.Np
+    base = np.asarray(mesh.EToB, dtype=np.int32).reshape(E, 6)
+    etob = np.stack([base, base, base]).copy()
+    etob[2][:, 5][etob[2][:, 5] > 0] = 4
+    lam0, lam1 = [1.0, 1.3, 0.8], [0.6, 0.5, 0.9]
+    opts = {"SOLVER": "PCG", "PRECONDITIONER": "JACOBI", "MAXIMUM ITERATIONS": "300", "SOLVER TOLERANCE": "1e-11"}
+    s = driver.OBlockSolver(mesh, opts, etob.reshape(-1), lam0, lam1, orc, stress_form=stress)
+    off, n = s.fieldOffset, E * Np
+    r = np.random.Generator(np.random.PCG64(3))
+    rhs = np.zeros(3 * off)
+    for f in range(3):
+        rhs[f * off:f * off + n] = r.random(n)
+    x = s.solve(rhs, np.zeros(3 * off))
+    Ax = np.zeros(3 * off)
+    s.ell.operator(x, Ax)
+    b = rhs.copy()
+    s.ell.apply_mask(b)
+    s.ell.gs(b)
+    assert 0 < s.Niter < 300
+    assert np.max(np.abs(Ax - b)) < 1e-9 * np.max(np.abs(b))
+    assert np.all(x[s.ell.mask_ids] == 0.0)
+    if not stress:   # block form: the Jacobi diagonal is exactly diag(A) (the stress form reuses it as an approximation)
+        for node in (5, n // 2, off + 17, 2 * off + n - 3):
+            e_ = np.zeros(3 * off)
+            e_[node] = 1.0
+            col = np.zeros(3 * off)
+            s.ell.ax(e_, col)
+            s.ell.gs(col)
+            # assembled diagonal entry of the global node = sum over its copies of the local diagonal entries
+            f, loc = divmod(node, off)
+            copies = np.flatnonzero(mesh.global_ids == mesh.global_ids[loc]) + f * off
+            ee = np.zeros(3 * off)
+            ee[copies] = 1.0
+            cc = np.zeros(3 * off)
+            s.ell.ax(ee, cc)
+            s.ell.gs(cc)
+            assert abs(cc[node] - 1.0 / s.inv_diag[node]) < 1e-10 * abs(cc[node])
