@@ -299,6 +299,10 @@ int nrsb_elliptic_operator_dot(nrsb_elliptic_t h, const double* d_q, double* d_A
  * engines); q_host / Aq_host should be pinned and must stay valid until nrsb_elliptic_host_wait returns */
 int nrsb_elliptic_operator_host_async(nrsb_elliptic_t h, const double* q_host, double* Aq_host);
 int nrsb_elliptic_host_wait(nrsb_elliptic_t h);
+/* device-side rendezvous of all ranks on the handle's stream (one scalar all-reduce through the peer windows, no host
+ * synchronisation): work queued behind it starts within an NVLink round trip on every GPU (MPI_Barrier leaves the
+ * ranks tens of microseconds apart: timeEllipticOperator, ellipticSetup.cpp:255-271, pays that once per sample) */
+int nrsb_elliptic_device_barrier(nrsb_elliptic_t h);
 /* ellipticAx on the full element list */
 int nrsb_elliptic_ax(nrsb_elliptic_t h, int level, int precision, const void* d_q, void* d_Aq);
 /* ellipticPreconditioner (ellipticPreconditioner.cpp:33-84) */

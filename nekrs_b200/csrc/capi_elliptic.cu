@@ -362,6 +362,19 @@ int nrsb_elliptic_operator_host_async(nrsb_elliptic_t h, const double* q_host, d
   return NRSB_OK;
 }
 
+// Device-side rendezvous of all ranks on the handle's stream (no host synchronisation): one scalar all-reduce
+// through the peer windows.  A host barrier leaves the ranks tens of microseconds apart; work queued behind this
+// launch starts within an NVLink round trip on every GPU.
+int nrsb_elliptic_device_barrier(nrsb_elliptic_t h)
+{
+  NRSB_REQUIRE(h, "handle is NULL");
+  elliptic_t& e = h->impl;
+  if (!e.comm || e.comm->nranks <= 1) return NRSB_OK;
+  int rc = fill_launch<double>(1, 0.0, e.o_scal.p + 7, e.stream);  // slot 7 = S_SUM (scratch)
+  if (rc) return rc;
+  return sum_launch<double>(1, e.o_scal.p + 7, e.o_scal.p + 7, e.ws, e.stream);
+}
+
 // Waits for every queued operator_host_async call (results are in the callers' host buffers afterwards);
 // the handle's stream is ordered after the downloads, so an event recorded on it next closes the timing.
 int nrsb_elliptic_host_wait(nrsb_elliptic_t h)

@@ -205,6 +205,10 @@ class Elliptic:
     def host_wait(self):
         call("nrsb_elliptic_host_wait", self._h)
 
+    def device_barrier(self):
+        """All ranks meet on the handle's stream (device-side all-reduce, no host synchronisation)."""
+        call("nrsb_elliptic_device_barrier", self._h)
+
     def ax(self, o_q, o_Aq, *, level=0, precision=8):
         call("nrsb_elliptic_ax", self._h, C.c_int(level), C.c_int(precision), vp(o_q), vp(o_Aq))
 
@@ -288,6 +292,9 @@ class OperatorBench:
     def timed_loop(self, fn, steps):
         """ms per call of `fn` over `steps` back-to-back calls (one event pair, launching stream)."""
         e0, e1, _ = self._ev
+        # several ranks: the host barrier before this call leaves the ranks tens of microseconds apart, which the first
+        # exchange of the timed region would absorb; meet on the device first (no-op on one rank), then start the clock
+        self.elliptic.device_barrier()
         e0.record()
         for _ in range(steps):
             fn()
