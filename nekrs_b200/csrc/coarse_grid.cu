@@ -346,9 +346,11 @@ int coarseSolver_t::plan_grid()
   gridSize = 0;
   const int n = replicated ? NTg : NT;
   if ((multiRank && !replicated) || n <= 0) return NRSB_OK;
-  int dev = 0, sms = 0;
+  int dev = 0, sms = 0, coop = 0;
   NRSB_CUDA(cudaGetDevice(&dev));
   NRSB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  NRSB_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+  if (!coop) return NRSB_OK;  // no co-residency guarantee: the cluster kernel or the multi-launch path take over
   int C = std::min(sms, (n + 63) / 64);
   const int RPC = ((n + C - 1) / C + 31) / 32 * 32;
   C = (n + RPC - 1) / RPC;
