@@ -68,6 +68,17 @@ def main():
                                           DB(like=r.random(E * 12 * Np)), D, DB(like=lam), DB(like=lam),
                                           DB(like=r.random(3 * off)), d_Aq)
     print("stress operator", float(np.abs(d_Aq.download()).max()) > 0)
+    # block solver through the handle (per-field masks, three-field gather-scatter, block reductions)
+    bm = meshgen.box_mesh(5, (3, 2, 2), kershaw_eps=0.3)
+    ob = {"SOLVER": "PCG", "PRECONDITIONER": "JACOBI", "MAXIMUM ITERATIONS": "5", "SOLVER TOLERANCE": "1e-12"}
+    eb = Elliptic(bm, ob, poisson=False, Nfields=3, stress_form=True, block_lambda0=[1.0, 1.2, 0.9],
+                  block_lambda1=[0.5, 0.6, 0.7], name="velocity")
+    offb, nb = eb.fieldOffset, bm.Nelements * bm.Np
+    rhs = np.zeros(3 * offb)
+    for f in range(3):
+        rhs[f * offb:f * offb + nb] = meshgen.kershaw_rhs(bm)
+    d_x = DB.zeros(3 * offb, np.float64)
+    print("block solver iterations", eb.solve(DB(like=rhs), d_x))
 
 
 if __name__ == "__main__":
