@@ -27,6 +27,10 @@ struct FdmV1 {
   static constexpr int Npe = Nrows * Nqe;
   static constexpr int TPE = Nrows / PPT;                 // threads per element
   static constexpr int smemFloats = 2 * Npe + 6 * Nqe * SP;
+  // one-element-per-warp form: as many whole elements as fit the 32 lanes (Nqe = 10: 1, 8: 2, 6: 3, 4: 8); their
+  // slabs are 8 floats apart beyond their size so that the elements of a warp start on different banks
+  static constexpr int EPW = TPE <= 32 ? 32 / TPE : 1;
+  static constexpr int warpStride = smemFloats + (EPW > 1 ? 8 : 0);
 };
 
 // two fp32 FMAs in one issue slot (Blackwell FFMA2; each half is an ordinary fma.rn, so the results are those of the
@@ -102,11 +106,12 @@ __global__ void __launch_bounds__((kWarp ? 32 : FdmV1<Nqe>::TPE) * EPB, (kWarp &
   constexpr int Npe = F::Npe;
   extern __shared__ __align__(16) float smem[];
   const int tid = threadIdx.x;
-  constexpr int TPB = kWarp ? 32 : F::TPE;  // threads per element slot of the block
-  const int t = tid % TPB;
-  const int es = tid / TPB;
-  const dlong e = blockIdx.x * EPB + es;
-  const bool lane = !kWarp || t < F::TPE;  // this thread owns pencils
+  // kWarp: EPB warps per block, each with EPW elements of TPE lanes; else EPB elements of TPE threads
+  constexpr int EPW = kWarp ? F::EPW : 1;
+  const int t = kWarp ? (tid % 32) % F::TPE : tid % F::TPE;
+  const int es = kWarp ? (tid / 32) * EPW + (tid % 32) / F::TPE : tid / F::TPE;
+  const dlong e = blockIdx.x * (EPB * EPW) + es;
+  const bool lane = !kWarp || (tid % 32) < EPW * F::TPE;  // this thread owns pencils
   const bool active = e < Nelements && lane;
   const dlong element = active ? elementList[e] : 0;
   auto sync = [] {
@@ -115,7 +120,7 @@ __global__ void __launch_bounds__((kWarp ? 32 : FdmV1<Nqe>::TPE) * EPB, (kWarp &
     else
       __syncthreads();
   };
-  float* A = smem + (size_t)es * F::smemFloats;
+  float* A = smem + (size_t)es * (kWarp ? F::warpStride : F::smemFloats);
   float* B = A + Npe;
   float* Sxf = B + Npe;  // forward  (row l: S[l][o])
   float* Syf = Sxf + Nqe * F::SP;
@@ -250,8 +255,9 @@ int launch_v1(int restrict_, dlong Nelements, const dlong* elementList, float* S
   constexpr int want = (192 + F::TPE - 1) / F::TPE;
   constexpr int EPB = EPBO ? EPBO : (want > 32 ? 32 : (want < 1 ? 1 : want));
   constexpr int TPB = kWarp ? 32 : F::TPE;
-  const size_t smem = (size_t)EPB * F::smemFloats * sizeof(float);
-  const int grid = (Nelements + EPB - 1) / EPB;
+  constexpr int EPW = kWarp ? F::EPW : 1;
+  const size_t smem = (size_t)EPB * EPW * (kWarp ? F::warpStride : F::smemFloats) * sizeof(float);
+  const int grid = (Nelements + EPB * EPW - 1) / (EPB * EPW);
   static bool configured[2] = {false, false};
   if (restrict_) {
     auto k = fused_fdm_v1_kernel<Nqe, true, EPB, kWarp>;
@@ -283,11 +289,17 @@ int fused_fdm_v1_launch(int Nq, int restrict_, dlong Nelements, const dlong* ele
 #define ARGS restrict_, Nelements, elementList, Su, Sx, Sy, Sz, invL, wts, u, stream
   if (Nq == 8 && warp) {
     switch (epb) {
-      case 1: return launch_v1<10, 1, true>(ARGS);
       case 2: return launch_v1<10, 2, true>(ARGS);
-      case 6: return launch_v1<10, 6, true>(ARGS);
       case 8: return launch_v1<10, 8, true>(ARGS);
       default: return launch_v1<10, 4, true>(ARGS);
+    }
+  }
+  if (warp && epb == 0) {  // the smaller even sizes: several elements per warp
+    switch (Nq + 2) {
+      case 4: return launch_v1<4, 4, true>(ARGS);
+      case 6: return launch_v1<6, 4, true>(ARGS);
+      case 8: return launch_v1<8, 4, true>(ARGS);
+      default: break;
     }
   }
   if (Nq == 8 && epb) {
