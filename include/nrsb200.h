@@ -37,6 +37,9 @@ typedef int64_t nrsb_hlong;
 
 const char* nrsb_last_error_string(void);
 const char* nrsb_version(void);
+/* sizeof of the structs of this header as the library was built ("nrsb_elliptic_config", "nrsb_shared_topology"; 0 for an
+ * unknown name): lets a binding written in another language check its mirror of the layout */
+int nrsb_sizeof(const char* struct_name);
 
 /* ---- device plumbing (platform->device.malloc / occa::memory::copyFrom/copyTo) ------------- */
 int nrsb_device_count(int* count);

@@ -91,6 +91,15 @@ static int out_dev(const T* p, size_t n, void* out, int64_t capacity, int64_t* c
 
 extern "C" {
 
+int nrsb_sizeof(const char* struct_name)
+{
+  if (!struct_name) return 0;
+  const std::string n(struct_name);
+  if (n == "nrsb_elliptic_config") return (int)sizeof(nrsb_elliptic_config);
+  if (n == "nrsb_shared_topology") return (int)sizeof(nrsb_shared_topology);
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------ comm
 int nrsb_comm_create(int rank, int nranks, nrsb_allgather_fn allgather, nrsb_barrier_fn barrier, void* user,
                      nrsb_comm_t* out)

@@ -45,3 +45,16 @@ def test_no_oracle_import_in_product():
                                                  or "CDLL" in line):
                             bad.append((fn, line.strip()))
     assert not bad, bad
+
+
+def test_python_mirror_of_the_config_structs_matches_the_library():
+    """The ctypes mirrors in nekrs_b200/elliptic.py against sizeof() as compiled into the library (a field added to
+    include/nrsb200.h but not to the mirror would shift every later member)."""
+    import ctypes as C
+    from nekrs_b200 import elliptic as E, lib
+    f = lib.load().nrsb_sizeof
+    f.restype = C.c_int
+    f.argtypes = [C.c_char_p]
+    assert f(b"nrsb_elliptic_config") == C.sizeof(E._Config)
+    assert f(b"nrsb_shared_topology") == C.sizeof(E._Topo)
+    assert f(b"no_such_struct") == 0
