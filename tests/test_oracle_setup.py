@@ -190,3 +190,27 @@ def test_diagonal_restatement_equals_unit_vector_probes_of_the_oracle_ax(orc):
         diag[n] = out[n]
     ref = K.build_diagonal(N, E, ggeo, D, lam0, lam1, poisson=False, lambda_field=True)
     assert np.max(np.abs(ref - diag)) / np.max(np.abs(diag)) < 1e-14
+
+
+def test_volume_factors_consistent_with_geometric_factors():
+    """mesh->vgeo of the oracle (oracle/driver.py::volume_factors, the input of the stress-form operator) against
+    the oracle's ggeo, which is pinned to the reference's geometricFactorsHex3D: G_ab = JW (grad a . grad b),
+    GWJ = JW (meshGeometricFactorsHex3D.cpp; ids mesh3D.h:82-102)."""
+    from nekrs_b200 import meshgen
+    from oracle import driver
+    from oracle.kernels import Orc
+    orc = Orc()
+    hm = meshgen.box_mesh(4, (2, 3, 2), kershaw_eps=0.3)
+    m = driver.OMesh(orc, hm.N, hm.Nelements, hm.x, hm.y, hm.z, hm.global_ids, hm.EToB)
+    v = driver.volume_factors(m)
+    g = m.ggeo.reshape(m.E, 7, m.Np)
+    r, s, t = v[:, 0:3], v[:, 3:6], v[:, 6:9]
+    JW = v[:, 10]
+    dot = lambda a, b: (a * b).sum(axis=1)
+    ref = {0: dot(r, r), 1: dot(r, s), 2: dot(s, s), 3: dot(s, t), 4: dot(r, t), 5: dot(t, t)}
+    scale = np.max(np.abs(g[:, :6]))
+    for k, val in ref.items():
+        assert np.max(np.abs(JW * val - g[:, k])) < 1e-12 * scale, k
+    assert np.max(np.abs(JW - g[:, 6])) < 1e-13 * np.max(np.abs(g[:, 6]))
+    assert np.all(v[:, 9] > 0) and np.allclose(v[:, 11] * JW, 1.0, rtol=1e-14)
+    assert abs(JW.sum() - 1.0) < 1e-12      # kershaw map of the unit box: volume 1
