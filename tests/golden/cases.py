@@ -54,6 +54,27 @@ def linalg_case():
     return dict(N=N, w=r.random(N), x=r.random(N), y=r.random(N), Ap=r.random(N), r=r.random(N), alpha=0.37)
 
 
+def block_case(N, stress, lambda_field):
+    """three-field operators: ellipticBlockPartialAxCoeffHex3D (ggeo) / ellipticStressPartialAxCoeffHex3D (vgeo)"""
+    E, Np = 4, (N + 1) ** 3
+    r = rng(9400 + 10 * N + (5 if stress else 0) + (1 if lambda_field else 0))
+    g, _ = sem.jacobi_gll(N)
+    D = sem.dmatrix_1d(g)
+    geo = (r.random((E, 12, Np)) - 0.3) if stress else r.random((E, 7, Np))
+    offset, loffset = E * Np + 16, E * Np + 8
+    q = r.random(3 * offset)
+    if lambda_field:
+        lam0, lam1 = r.random(3 * loffset) + 0.5, r.random(3 * loffset)
+    else:
+        lam0, lam1 = np.zeros(3 * loffset), np.zeros(3 * loffset)
+        lam0[[0, loffset, 2 * loffset]] = [1.1, 1.2, 1.3]
+        lam1[[0, loffset, 2 * loffset]] = [0.5, 0.6, 0.7]
+    el = np.array([2, 0, 3], dtype=np.int32)
+    return dict(N=N, E=E, Np=Np, D=D, geo=geo, q=q, el=el, lam0=lam0, lam1=lam1, offset=offset, loffset=loffset,
+                stress=stress, lambda_field=lambda_field)
+
+
+BLOCK_CASES = [(7, False, False), (7, True, False), (3, True, True), (3, False, True)]
 AX_CASES = [(7, "d", True), (7, "f", True), (3, "f", True), (1, "f", True), (7, "d", False), (5, "d", True)]
 FDM_CASES = [(7, 1), (3, 1), (7, 0)]
 TRANSFER_CASES = [(7, 3), (3, 1)]

@@ -30,6 +30,12 @@ def main():
         else:
             K.RefAx(N, prec, poisson=False)(c["el"], c["ggeo"], c["D"], c["q"], a, c["lam0"], c["lam1"])
         out["ax_N%d_%s_%s" % (N, prec, "poisson" if poisson else "helmholtz")] = a
+    for N, stress, lf in cases.BLOCK_CASES:
+        c = cases.block_case(N, stress, lf)
+        a = np.full(3 * c["offset"], -7.0)
+        ref = (K.RefAxStress if stress else K.RefAxBlock)(N, lf)
+        ref(c["el"], c["geo"], c["D"], c["q"], a, c["lam0"], c["lam1"], c["offset"], c["loffset"])
+        out["%s_N%d_lambda%d" % ("axstress" if stress else "axblock", N, int(lf))] = a
     for N, restrict in cases.FDM_CASES:
         c = cases.fdm_case(N, restrict)
         ref = K.RefFdm(N, restrict)

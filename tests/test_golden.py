@@ -23,6 +23,15 @@ def test_ax(orc, N, prec, poisson):
     assert np.all(gold.reshape(c["E"], c["Np"])[1] == -7.0)  # element 1 is not in the list
 
 
+@pytest.mark.parametrize("N,stress,lf", cases.BLOCK_CASES)
+def test_block_and_stress_ax(orc, N, stress, lf):
+    c = cases.block_case(N, stress, lf)
+    b = np.full(3 * c["offset"], -7.0)
+    fn = orc.ax_stress if stress else orc.ax_block
+    fn(N, c["el"], c["geo"], c["D"], c["q"], b, c["lam0"], c["lam1"], c["offset"], c["loffset"], lambda_field=lf)
+    assert np.array_equal(b, GOLD["%s_N%d_lambda%d" % ("axstress" if stress else "axblock", N, int(lf))])
+
+
 @pytest.mark.parametrize("N,restrict", cases.FDM_CASES)
 def test_fdm(orc, N, restrict):
     c = cases.fdm_case(N, restrict)

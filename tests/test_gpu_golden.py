@@ -34,6 +34,21 @@ def test_ax(N, prec, poisson, variant):
     assert np.all(out.reshape(c["E"], c["Np"])[1] == -7.0)  # unlisted element untouched
 
 
+@pytest.mark.parametrize("N,stress,lf", cases.BLOCK_CASES)
+def test_block_and_stress_ax(N, stress, lf):
+    """The three-field operators against the outputs of the reference's own block / stress kernels."""
+    c = cases.block_case(N, stress, lf)
+    d_Aq = DB(like=np.full(3 * c["offset"], -7.0))
+    fn = ops.ellipticStressPartialAxCoeffHex3D if stress else ops.ellipticBlockPartialAxCoeffHex3D
+    fn(N, c["el"].size, c["offset"], c["loffset"], DB(like=c["el"]), DB(like=c["geo"]), c["D"], DB(like=c["lam0"]),
+       DB(like=c["lam1"]), DB(like=c["q"]), d_Aq, lambda_field=lf)
+    gold = GOLD["%s_N%d_lambda%d" % ("axstress" if stress else "axblock", N, int(lf))]
+    out = d_Aq.download()
+    assert relerr(out, gold) < 1e-12
+    for f in range(3):   # unlisted element untouched, in every field
+        assert np.all(out[f * c["offset"]:f * c["offset"] + c["E"] * c["Np"]].reshape(c["E"], c["Np"])[1] == -7.0)
+
+
 @pytest.mark.parametrize("N,restrict", cases.FDM_CASES)
 def test_fdm(N, restrict):
     c = cases.fdm_case(N, restrict)
